@@ -1,0 +1,203 @@
+// Shared device helpers for libgvcnn_sm100.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gvcnn_b200.h"
+
+namespace gvcnn {
+
+// V base pointers (bytes), one per view, passed by value as a kernel parameter
+// (1 KB).  Every layout the ABI accepts reduces to "row (b, v) starts at
+// p[v] + b * stride_b": BVD p[v] = X + v*D, stride_b = V*D; VBD p[v] = X + v*B*D,
+// stride_b = D; PTRS p[v] = the caller's v-th pointer, stride_b = D.
+struct ViewPtrs {
+    char *p[GVCNN_MAX_VIEWS];
+};
+
+// Per-shape view plan in shared memory: views sorted by (bin, view index).
+// Both the forward and the backward kernel derive it from the same bins, so
+// tie-mask bit k means the same view in both.
+struct Plan {
+    int32_t rawbin[GVCNN_MAX_VIEWS];  // v -> clamped bin
+    int32_t gbin[GVCNN_MAX_VIEWS];    // k -> bin of the k-th sorted view
+    float gw[GVCNN_MAX_VIEWS];        // k -> weight of that group (1 + n_g unless given)
+    float sumw;                       // sum of all G weights (G + V unless given)
+    uint16_t glen[GVCNN_MAX_VIEWS];   // k -> size of the group the k-th view is in
+    uint8_t order[GVCNN_MAX_VIEWS];   // k -> v
+};
+
+// Builds the plan for one shape.  Must be called by all threads of the CTA
+// (contains __syncthreads); needs blockDim.x >= 32 and handles V up to 128 by
+// striding.  Bins outside [0, G) are counted into status and clamped.
+// `weights` (nullable) is this shape's row of G caller-supplied group weights
+// (model.group_fusion's second argument); null means the reference's own
+// group_weight, 1 + n_g, whose sum G + V is exact in float32 in any order.
+__device__ __forceinline__ void build_plan(Plan &pl, const int32_t *__restrict__ bins, int V, int G,
+                                           int32_t *status, const float *__restrict__ weights = nullptr)
+{
+    if (threadIdx.x == 0) {
+        float sw = (float)(G + V);
+        if (weights) {  // tf.reduce_sum(group_weight_list), left to right
+            sw = 0.0f;
+            for (int g = 0; g < G; ++g) sw = __fadd_rn(sw, __ldg(weights + g));
+        }
+        pl.sumw = sw;
+    }
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        int b = __ldg(bins + v);
+        if (b < 0 || b >= G) {
+            if (status) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+            b = b < 0 ? 0 : G - 1;
+        }
+        pl.rawbin[v] = b;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const int b = pl.rawbin[v];
+        int below = 0, same_before = 0, same = 0;
+        for (int u = 0; u < V; ++u) {
+            const int bu = pl.rawbin[u];
+            below += (bu < b);
+            same += (bu == b);
+            same_before += (bu == b) & (u < v);
+        }
+        const int k = below + same_before;
+        pl.order[k] = (uint8_t)v;
+        pl.gbin[k] = b;
+        pl.glen[k] = (uint16_t)same;
+        pl.gw[k] = weights ? __ldg(weights + b) : (float)(1 + same);
+    }
+    __syncthreads();
+}
+
+// ---- memory helpers --------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_16(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_16(void *p, const uint4 &v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// mbarrier + bulk async copy (TMA engine, 1-D form: no tensor map needed since
+// every (shape, view) row is contiguous in all three layouts).
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- element packing ---------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kVec = 4;  // elements per 16-byte vector
+    __device__ static __forceinline__ void unpack(const uint4 &r, float (&f)[4])
+    {
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+        f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    }
+    __device__ static __forceinline__ uint4 pack(const float (&f)[4])
+    {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                          __float_as_uint(f[3]));
+    }
+    __device__ static __forceinline__ float to_float(float v) { return v; }
+    __device__ static __forceinline__ float from_float(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kVec = 8;
+    __device__ static __forceinline__ void unpack(const uint4 &r, float (&f)[8])
+    {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ uint4 pack(const float (&f)[8])
+    {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i]));
+            const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i + 1]));
+            w[i] = lo | (hi << 16);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ---- launchers implemented in the .cu files ----------------------------------
+int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,
+                      float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int C,
+                      int G, int dtype, bool aligned16, bool fuse_bin, int edge_ulps, int clamp,
+                      cudaStream_t st);
+int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st);
+int launch_score_bin(const float *x, float denom, float *scores, int32_t *bins, int32_t *flags,
+                     int32_t *status, int64_t n, int G, int edge_ulps, int clamp, bool x_is_score,
+                     cudaStream_t st);
+int launch_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, cudaStream_t st);
+int launch_scheme_to_bins(const int32_t *scheme, int32_t *bins, int32_t *status, int rows, int V, int G,
+                          cudaStream_t st);
+int launch_group_weight(const int32_t *bins, float *weights, int rows, int V, int G, cudaStream_t st);
+int launch_pool_fuse_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                         void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool,
+                         float fill, int dtype, bool aligned16, int variant, cudaStream_t st);
+int launch_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                         const float *weights, int64_t w_sb,
+                         const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                         int pool, int dtype, bool aligned16, cudaStream_t st);
+
+}  // namespace gvcnn

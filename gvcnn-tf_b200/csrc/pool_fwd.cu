@@ -1,0 +1,248 @@
+// Pooling + fusion forward: nets/model.py:28-41 (w_g = 1 + n_g), :44-74
+// (view_pooling) and :77-102 (group_fusion) in ONE pass over F.
+//
+// Shape of the work: for every (shape b, descriptor element d) reduce V values
+// (12) to one - a streaming reduction at ~0.25 flop/byte, HBM-bound.  One CTA
+// owns a tile of TD consecutive descriptor elements of one shape.  Thread 0
+// fires V 1-D bulk async copies (cp.async.bulk = the TMA engine; every
+// (shape, view) row is contiguous in all accepted layouts, so no tensor map is
+// needed) that land the V x TD slab in shared memory in NATURAL view order -
+// independent of the bins - while the whole CTA loads the shape's V bins and
+// counting-sorts the views by (bin, view).  Each thread then walks its 16-byte
+// column of the slab group by group in bin order with float32 registers:
+//     m   = max | sum over the group's views          (exact | left to right)
+//     acc = acc + w_g * m      (__fmul_rn, __fadd_rn: one rounding per op)
+// empty groups add `empty_fill` in their place in the order, and
+// S = acc / (G + V) with one IEEE division - the reference's op order, so the
+// float32 result is bit-identical to the oracle's.  Several CTAs are resident
+// per SM (48 KB of slab each at V = 12), which is what keeps ~150 KB of loads
+// in flight per SM; no thread ever waits on a global load directly.
+//
+// Max-mode training additionally writes the tie mask (one more pass over the
+// group's slab columns in shared memory, not in HBM).
+#include "common.cuh"
+
+namespace gvcnn {
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_col(const T *stage, int v, int TD, int e0,
+                                         float (&f)[VEC ? Elem<T>::kVec : 1])
+{
+    if constexpr (VEC) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(stage + (size_t)v * TD + e0);
+        Elem<T>::unpack(raw, f);
+    } else {
+        f[0] = Elem<T>::to_float(stage[(size_t)v * TD + e0]);
+    }
+}
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void store_fill(T *dst, float fill)
+{
+    if constexpr (VEC) {
+        float f[Elem<T>::kVec];
+#pragma unroll
+        for (int e = 0; e < Elem<T>::kVec; ++e) f[e] = fill;
+        stg_stream_16(dst, Elem<T>::pack(f));
+    } else {
+        *dst = Elem<T>::from_float(fill);
+    }
+}
+
+template <typename T, bool VEC, int POOL, bool MASK, bool BULK>
+__global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
+                                     const int64_t bin_sb, T *__restrict__ S, T *__restrict__ Pout,
+                                     uint8_t *__restrict__ mask, const float *__restrict__ weights,
+                                     const int64_t w_sb, int32_t *status, const int B, const int V, const int64_t D, const int G,
+                                     const float fill, const int tiles_per_shape)
+{
+    constexpr int E = VEC ? Elem<T>::kVec : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ Plan plan;
+    __shared__ __align__(8) uint64_t bar;
+
+    const int NT = blockDim.x;
+    const int TD = NT * E;
+    const int b = blockIdx.x / tiles_per_shape;
+    const int tile = blockIdx.x - b * tiles_per_shape;
+    const int64_t d0 = (int64_t)tile * TD;
+    const int n_valid = (int)min((int64_t)TD, D - d0);
+    T *stage = reinterpret_cast<T *>(smem_raw);  // [V][TD]
+    const int e0 = threadIdx.x * E;
+
+    if constexpr (BULK) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+            const uint32_t row_bytes = (uint32_t)n_valid * sizeof(T);
+            mbar_expect_tx(&bar, row_bytes * (uint32_t)V);
+            for (int v = 0; v < V; ++v)
+                bulk_g2s(stage + (size_t)v * TD, reinterpret_cast<const T *>(fp.p[v]) + (int64_t)b * f_sb + d0,
+                         row_bytes, &bar);
+        }
+    } else {
+        if (e0 < n_valid) {
+            for (int v = 0; v < V; ++v) {
+                const T *src = reinterpret_cast<const T *>(fp.p[v]) + (int64_t)b * f_sb + d0 + e0;
+                if constexpr (VEC)
+                    *reinterpret_cast<uint4 *>(stage + (size_t)v * TD + e0) = ldg_stream_16(src);
+                else
+                    stage[(size_t)v * TD + e0] = *src;
+            }
+        }
+    }
+
+    const float *wrow = weights ? weights + (int64_t)b * w_sb : nullptr;
+    build_plan(plan, bins + (int64_t)b * bin_sb, V, G, status, wrow);  // two __syncthreads inside
+    if constexpr (BULK) mbar_wait(&bar, 0);
+    if (e0 >= n_valid) return;
+
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+    uint32_t pw[(E + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (E + 3) / 4; ++i) pw[i] = 0u;
+
+    const int64_t out_off = (int64_t)b * D + d0 + e0;
+    int k = 0, prev_g = -1;
+    while (k < V) {
+        const int g = plan.gbin[k];
+        const int len = plan.glen[k];
+        if (fill != 0.0f)
+            for (int q = prev_g + 1; q < g; ++q) {  // empty groups: w = 1 (or given), P = fill
+                const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+            }
+        if (Pout)
+            for (int q = prev_g + 1; q < g; ++q) store_fill<T, VEC>(Pout + ((int64_t)q * B) * D + out_off, fill);
+        float m[E];
+        load_col<T, VEC>(stage, plan.order[k], TD, e0, m);
+        for (int j = 1; j < len; ++j) {
+            float x[E];
+            load_col<T, VEC>(stage, plan.order[k + j], TD, e0, x);
+#pragma unroll
+            for (int e = 0; e < E; ++e) m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+        }
+        const float w = plan.gw[k];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)len);
+            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+        }
+        if (Pout) {
+            T *pp = Pout + ((int64_t)g * B) * D + out_off;
+            if constexpr (VEC) stg_stream_16(pp, Elem<T>::pack(m));
+            else *pp = Elem<T>::from_float(m[0]);
+        }
+        if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+            for (int j = 0; j < len; ++j) {
+                const int kk = k + j;
+                float x[E];
+                load_col<T, VEC>(stage, plan.order[kk], TD, e0, x);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    pw[e >> 2] |= (uint32_t)(x[e] == m[e]) << (8 * (e & 3) + (kk & 7));
+                if ((kk & 7) == 7 || kk == V - 1) {
+                    uint8_t *mp = mask + ((int64_t)(kk >> 3) * B) * D + out_off;
+                    if constexpr (E == 8) {
+                        *reinterpret_cast<uint2 *>(mp) = make_uint2(pw[0], pw[1]);
+                        pw[0] = pw[1] = 0u;
+                    } else if constexpr (E == 4) {
+                        *reinterpret_cast<uint32_t *>(mp) = pw[0];
+                        pw[0] = 0u;
+                    } else {
+                        *mp = (uint8_t)pw[0];
+                        pw[0] = 0u;
+                    }
+                }
+            }
+        }
+        prev_g = g;
+        k += len;
+    }
+    if (fill != 0.0f)
+        for (int q = prev_g + 1; q < G; ++q) {
+            const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+        }
+    if (Pout)
+        for (int q = prev_g + 1; q < G; ++q) store_fill<T, VEC>(Pout + ((int64_t)q * B) * D + out_off, fill);
+    const float sumw = plan.sumw;  // G + V for the reference's weights (exact in any order)
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = __fdiv_rn(acc[e], sumw);
+    if constexpr (VEC)
+        stg_stream_16(S + out_off, Elem<T>::pack(acc));
+    else
+        S[out_off] = Elem<T>::from_float(acc[0]);
+}
+
+// threads per CTA: the largest of 256/128/64/32 whose slab fits ~56 KB (so >= 4
+// CTAs share an SM), but never more than one tile row needs.
+static int pick_threads(int V, int64_t D, int E, size_t elt, size_t budget)
+{
+    int nt = 256;
+    while (nt > 32 && (size_t)V * nt * E * elt > budget) nt >>= 1;
+    const int64_t need = (D + E - 1) / E;
+    while (nt > 32 && nt / 2 >= need) nt >>= 1;
+    return nt;
+}
+
+template <typename T>
+static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                        void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
+                        bool vec, int variant, cudaStream_t st)
+{
+    const int E = vec ? Elem<T>::kVec : 1;
+    const int nt = pick_threads(V, D, E, sizeof(T), 56 * 1024);
+    const size_t smem = (size_t)V * nt * E * sizeof(T);
+    if (smem > 200 * 1024) return GVCNN_E_TOO_MANY_VIEWS;
+    const int64_t td = (int64_t)nt * E;
+    const int64_t tiles = (D + td - 1) / td;
+    if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
+    const bool bulk = vec && variant != 2;
+    const bool want_mask = (mask != nullptr) && pool == GVCNN_POOL_MAX;
+    cudaError_t err = cudaSuccess;
+#define GVCNN_LAUNCH_FWD(VEC_, POOL_, MASK_, BULK_)                                                        \
+    do {                                                                                                   \
+        auto kern = pool_fuse_fwd_kernel<T, VEC_, POOL_, MASK_, BULK_>;                                    \
+        if (smem > 48 * 1024)                                                                              \
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (err == cudaSuccess)                                                                            \
+            kern<<<(unsigned)(B * tiles), nt, smem, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),      \
+                                                          static_cast<T *>(Pout), mask, weights, w_sb,     \
+                                                          status, B, V, D, G, fill, (int)tiles);           \
+    } while (0)
+    if (vec) {
+        if (pool == GVCNN_POOL_MAX) {
+            if (want_mask) { if (bulk) GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MAX, true, true); else GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MAX, true, false); }
+            else           { if (bulk) GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MAX, false, true); else GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MAX, false, false); }
+        } else {
+            if (bulk) GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MEAN, false, true); else GVCNN_LAUNCH_FWD(true, GVCNN_POOL_MEAN, false, false);
+        }
+    } else {
+        if (pool == GVCNN_POOL_MAX) {
+            if (want_mask) GVCNN_LAUNCH_FWD(false, GVCNN_POOL_MAX, true, false); else GVCNN_LAUNCH_FWD(false, GVCNN_POOL_MAX, false, false);
+        } else {
+            GVCNN_LAUNCH_FWD(false, GVCNN_POOL_MEAN, false, false);
+        }
+    }
+#undef GVCNN_LAUNCH_FWD
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaGetLastError();
+}
+
+int launch_pool_fuse_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                         void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
+                         int dtype, bool aligned16, int variant, cudaStream_t st)
+{
+    if (dtype == GVCNN_F32)
+        return launch_fwd_t<float>(fp, f_sb, bins, bin_sb, S, Pout, mask, weights, w_sb, status, B, V, D, G, pool, fill,
+                                   aligned16 && D % 4 == 0, variant, st);
+    return launch_fwd_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, S, Pout, mask, weights, w_sb, status, B, V, D, G, pool, fill,
+                                       aligned16 && D % 8 == 0, variant, st);
+}
+
+}  // namespace gvcnn

@@ -1,0 +1,215 @@
+// Score + binning kernels: nets/model.py:144-147 (per-view Dense(1) on the raw
+// descriptor, sigmoid(log|x|)) and :23 (bin = int(score * G)).
+//
+// Shape of the work: B*V independent dot products of length C (1024) against
+// V weight rows - a batch of GEMVs with 0.5 flop/byte, so HBM-bound; one warp
+// per (shape, view) row, 128-bit streaming loads of R, W served from L1/L2
+// (V*C*4 = 48 KB total), xor-butterfly reduction, everything after the dot
+// product fused into lane 0's epilogue.  The summation order is fixed and is
+// restated in oracle/gvcnn_oracle.c (oracle_view_score_x_kernel_order):
+//   lane l accumulates chunks (i*32 + l) of E consecutive elements with one
+//   fmaf chain, lanes combine with offsets 16,8,4,2,1, bias is added last.
+#include "common.cuh"
+
+namespace gvcnn {
+
+// s = |x| / (1 + |x|) == sigmoid(log|x|); bin = (int)(s * G) with a float32
+// product (NumPy scalar semantics of model.py:23).  Returns the flag bits.
+__device__ __forceinline__ int score_and_bin(float x, float denom, int G, int edge_ulps, int clamp,
+                                             float &s_out, int &bin_out, bool x_is_score = false)
+{
+    const float xm = __fdiv_rn(x, denom);
+    const float ax = fabsf(xm);
+    float s = x_is_score ? x : (isinf(ax) ? 1.0f : __fdiv_rn(ax, __fadd_rn(1.0f, ax)));
+    int flags = 0;
+    int bin;
+    const float fg = (float)G;
+    if (isnan(s)) {
+        flags |= GVCNN_FLAG_NAN;
+        bin = clamp ? 0 : INT32_MIN;
+    } else {
+        bin = (int)__fmul_rn(s, fg);
+        if (edge_ulps > 0) {
+            const uint32_t bits = __float_as_uint(s);  // s in [0, 1]: ordered as integers
+            const uint32_t lo = bits > (uint32_t)edge_ulps ? bits - edge_ulps : 0u;
+            const uint32_t hi = bits + edge_ulps;
+            if ((int)__fmul_rn(__uint_as_float(lo), fg) != bin ||
+                (int)__fmul_rn(__uint_as_float(hi), fg) != bin)
+                flags |= GVCNN_FLAG_NEAR_EDGE;
+        }
+        if (bin >= G) {
+            flags |= GVCNN_FLAG_BIN_RANGE;
+            if (clamp) bin = G - 1;
+        }
+    }
+    s_out = s;
+    bin_out = bin;
+    return flags;
+}
+
+__device__ __forceinline__ void publish(int flags, int32_t *flag_out, int32_t *status)
+{
+    if (flag_out) *flag_out = flags;
+    if (status && flags) {
+        if (flags & GVCNN_FLAG_BIN_RANGE) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+        if (flags & GVCNN_FLAG_NAN) atomicAdd(status + GVCNN_STATUS_NAN, 1);
+        if (flags & GVCNN_FLAG_NEAR_EDGE) atomicAdd(status + GVCNN_STATUS_NEAR_EDGE, 1);
+    }
+}
+
+constexpr int kScoreWarps = 8;
+constexpr int kScoreUnroll = 8;  // 16-byte loads in flight per lane per pass
+
+// One warp per (b, v) row.  VEC: 16-byte loads (E = 16/sizeof(T) elements per
+// chunk) when rows are 16-byte aligned and C % E == 0, else E = 1.
+template <typename T, bool VEC, bool FUSE_BIN>
+__global__ void __launch_bounds__(kScoreWarps * 32)
+view_score_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict__ W,
+                  const float *__restrict__ bias, float *__restrict__ x_out, float *__restrict__ scores,
+                  int32_t *__restrict__ bins, int32_t *__restrict__ flag_out, int32_t *status, const int B,
+                  const int V, const int C, const int G, const int edge_ulps, const int clamp)
+{
+    constexpr int E = VEC ? Elem<T>::kVec : 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kScoreWarps + (threadIdx.x >> 5);
+    if (row >= (int64_t)B * V) return;
+    const int b = (int)(row / V);
+    const int v = (int)(row - (int64_t)b * V);
+    const T *__restrict__ r = reinterpret_cast<const T *>(rp.p[v]) + (int64_t)b * r_sb;
+    const float *__restrict__ w = W + (int64_t)v * C;
+
+    float acc = 0.0f;
+    if constexpr (VEC) {
+        for (int base0 = lane * E; base0 < C; base0 += 32 * E * kScoreUnroll) {
+            uint4 raw[kScoreUnroll];
+#pragma unroll
+            for (int u = 0; u < kScoreUnroll; ++u) {
+                const int base = base0 + u * 32 * E;
+                if (base < C) raw[u] = ldg_stream_16(r + base);
+            }
+#pragma unroll
+            for (int u = 0; u < kScoreUnroll; ++u) {
+                const int base = base0 + u * 32 * E;
+                if (base < C) {
+                    float f[E];
+                    Elem<T>::unpack(raw[u], f);
+#pragma unroll
+                    for (int j = 0; j < E; j += 4) {
+                        const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + base + j));
+                        acc = fmaf(f[j + 0], wv.x, acc);
+                        acc = fmaf(f[j + 1], wv.y, acc);
+                        acc = fmaf(f[j + 2], wv.z, acc);
+                        acc = fmaf(f[j + 3], wv.w, acc);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) acc = fmaf(Elem<T>::to_float(r[c]), __ldg(w + c), acc);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+
+    if (lane == 0) {
+        const float x = __fadd_rn(acc, __ldg(bias + v));
+        if (x_out) x_out[row] = x;
+        if constexpr (FUSE_BIN) {
+            float s;
+            int bin;
+            const int flags = score_and_bin(x, 1.0f, G, edge_ulps, clamp, s, bin);
+            scores[row] = s;
+            bins[row] = bin;
+            publish(flags, flag_out ? flag_out + row : nullptr, status);
+        }
+    }
+}
+
+// xsum[v] = sum_b x[b, v], fixed order: thread t adds b = t, t+256, ... in
+// sequence, warps butterfly, thread 0 adds the 8 warp sums in warp order.
+__global__ void __launch_bounds__(256) batch_sum_x_kernel(const float *__restrict__ x,
+                                                          float *__restrict__ xsum, const int B, const int V)
+{
+    __shared__ float warp_sum[8];
+    const int v = blockIdx.x;
+    float acc = 0.0f;
+    for (int b = threadIdx.x; b < B; b += 256) acc = __fadd_rn(acc, x[(int64_t)b * V + v]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = warp_sum[0];
+        for (int i = 1; i < 8; ++i) t = __fadd_rn(t, warp_sum[i]);
+        xsum[v] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) score_bin_kernel(const float *__restrict__ x, const float denom,
+                                                        float *__restrict__ scores,
+                                                        int32_t *__restrict__ bins,
+                                                        int32_t *__restrict__ flag_out, int32_t *status,
+                                                        const int64_t n, const int G, const int edge_ulps,
+                                                        const int clamp, const bool x_is_score)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float s;
+    int bin;
+    const int flags = score_and_bin(x[i], denom, G, edge_ulps, clamp, s, bin, x_is_score);
+    if (scores) scores[i] = s;
+    bins[i] = bin;
+    publish(flags, flag_out ? flag_out + i : nullptr, status);
+}
+
+template <typename T>
+static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,
+                               float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V,
+                               int C, int G, bool vec, bool fuse_bin, int edge_ulps, int clamp,
+                               cudaStream_t st)
+{
+    const int64_t rows = (int64_t)B * V;
+    const dim3 grid((unsigned)((rows + kScoreWarps - 1) / kScoreWarps)), block(kScoreWarps * 32);
+#define GVCNN_LAUNCH_SCORE(VEC_, FUSE_)                                                               \
+    view_score_kernel<T, VEC_, FUSE_><<<grid, block, 0, st>>>(rp, r_sb, W, bias, x, scores, bins, flags, \
+                                                             status, B, V, C, G, edge_ulps, clamp)
+    if (vec) {
+        if (fuse_bin) GVCNN_LAUNCH_SCORE(true, true); else GVCNN_LAUNCH_SCORE(true, false);
+    } else {
+        if (fuse_bin) GVCNN_LAUNCH_SCORE(false, true); else GVCNN_LAUNCH_SCORE(false, false);
+    }
+#undef GVCNN_LAUNCH_SCORE
+    return (int)cudaGetLastError();
+}
+
+int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,
+                      float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int C,
+                      int G, int dtype, bool aligned16, bool fuse_bin, int edge_ulps, int clamp,
+                      cudaStream_t st)
+{
+    if (dtype == GVCNN_F32) {
+        const bool vec = aligned16 && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+        return launch_view_score_t<float>(rp, r_sb, W, bias, x, scores, bins, flags, status, B, V, C, G, vec,
+                                          fuse_bin, edge_ulps, clamp, st);
+    }
+    const bool vec = aligned16 && (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    return launch_view_score_t<__nv_bfloat16>(rp, r_sb, W, bias, x, scores, bins, flags, status, B, V, C, G,
+                                              vec, fuse_bin, edge_ulps, clamp, st);
+}
+
+int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st)
+{
+    batch_sum_x_kernel<<<V, 256, 0, st>>>(x, xsum, B, V);
+    return (int)cudaGetLastError();
+}
+
+int launch_score_bin(const float *x, float denom, float *scores, int32_t *bins, int32_t *flags,
+                     int32_t *status, int64_t n, int G, int edge_ulps, int clamp, bool x_is_score,
+                     cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    score_bin_kernel<<<grid, 256, 0, st>>>(x, denom, scores, bins, flags, status, n, G, edge_ulps, clamp,
+                                           x_is_score);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace gvcnn

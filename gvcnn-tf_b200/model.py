@@ -1,0 +1,571 @@
+"""Host-side mirror of the reference's ``nets/model.py`` for the grouping + fusion path.
+
+Same function names, positional arguments and error behaviour as the reference
+(``group_scheme``, ``group_weight``, ``view_pooling``, ``group_fusion``,
+``gvcnn`` head), operating on torch CUDA tensors and calling the sm_100a
+kernels of ``libgvcnn_sm100.so`` through ctypes (``_cabi.py``).  torch is used
+for device memory, streams and autograd plumbing only; all arithmetic of the
+path runs in the library.  There is no CPU path and no fallback: a non-CUDA
+tensor or a missing library raises.
+
+Reference map (all in /root/reference):
+  group_scheme   nets/model.py:16-25   (caller: train.py:277, eval.py:191)
+  group_weight   nets/model.py:28-41   (caller: train.py:278, eval.py:192)
+  view_pooling   nets/model.py:44-74   (caller: nets/model.py:154)
+  group_fusion   nets/model.py:77-102  (caller: nets/model.py:157)
+  view scores    nets/model.py:144-148
+  gvcnn head     nets/model.py:143-166
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi as C
+
+__all__ = [
+    "group_scheme", "group_weight", "view_pooling", "group_fusion", "view_scores",
+    "score_bin", "pool_fuse", "grouping_fusion", "GroupDescriptors", "ScoreResult",
+    "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status",
+]
+
+_POOL = {"max": C.POOL_MAX, "mean": C.POOL_MEAN}
+
+
+# --------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return C.F32
+    if dt == torch.bfloat16:
+        return C.BF16
+    raise TypeError("gvcnn_b200 supports float32 and bfloat16 descriptors, got %s" % dt)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device: gvcnn_b200 has no CPU path" % name)
+
+
+class _Views:
+    """A per-view tensor (R, F or dF) in any accepted layout, reduced to what the
+    C ABI wants: (pointer argument, layout code, B, V, D)."""
+
+    def __init__(self, x, layout: Optional[str], name: str):
+        self.keep = []
+        if isinstance(x, (list, tuple)):                      # the reference's Python list of views
+            if len(x) == 0:
+                raise ValueError("%s: empty view list" % name)
+            for t in x:
+                _require_cuda(t, name)
+            first = x[0]
+            views = []
+            for t in x:
+                if t.shape != first.shape or t.dtype != first.dtype or t.device != first.device:
+                    raise ValueError("%s: all views must share shape, dtype and device" % name)
+                views.append(t if t.is_contiguous() else t.contiguous())
+            self.keep = views
+            self.V = len(views)
+            self.B = first.shape[0] if first.dim() > 0 else 1
+            self.D = int(first.numel() // max(self.B, 1))
+            self.view_shape = tuple(first.shape)
+            self.dtype, self.device = first.dtype, first.device
+            self.layout = C.LAYOUT_PTRS
+            self.table = (ctypes.c_void_p * self.V)(*[t.data_ptr() for t in views])
+            self.arg = ctypes.cast(self.table, ctypes.c_void_p)
+            self.kind = "list"
+        else:
+            _require_cuda(x, name)
+            if x.dim() < 3:
+                raise ValueError("%s: expected [B, V, ...] or [V, B, ...], got shape %s" % (name, tuple(x.shape)))
+            t = x if x.is_contiguous() else x.contiguous()
+            self.keep = [t]
+            layout = layout or "bvd"
+            if layout == "bvd":
+                self.B, self.V = t.shape[0], t.shape[1]
+                self.layout = C.LAYOUT_BVD
+            elif layout == "vbd":
+                self.V, self.B = t.shape[0], t.shape[1]
+                self.layout = C.LAYOUT_VBD
+            else:
+                raise ValueError("layout must be 'bvd' or 'vbd'")
+            self.D = int(t.numel() // (self.B * self.V)) if self.B * self.V else 0
+            self.view_shape = (self.B,) + tuple(t.shape[2:])
+            self.dtype, self.device = t.dtype, t.device
+            self.arg = ctypes.c_void_p(t.data_ptr())
+            self.kind = layout
+            self.tensor = t
+        if self.B <= 0 or self.V <= 0 or self.D <= 0:
+            raise ValueError("%s: empty tensor (B=%d, V=%d, D=%d)" % (name, self.B, self.V, self.D))
+        if self.V > C.MAX_VIEWS:
+            raise ValueError("%s: at most %d views are supported, got %d" % (name, C.MAX_VIEWS, self.V))
+
+    def empty_like(self):
+        """Fresh storage of the same layout (for dF)."""
+        if self.kind == "list":
+            out = [torch.empty_like(t) for t in self.keep]
+            v = _Views(out, None, "dF")
+            return out, v
+        out = torch.empty_like(self.tensor)
+        return out, _Views(out, self.kind, "dF")
+
+
+def raise_for_status(status: torch.Tensor, num_group: int):
+    """Turns the device status words into the reference's exceptions
+    (nets/model.py:23): NaN score -> ValueError, bin >= num_group -> IndexError.
+    Synchronises (one 16-byte device->host copy)."""
+    st = status.tolist()
+    if st[C.STATUS_NAN]:
+        raise ValueError("cannot convert float NaN to integer (%d NaN view scores)" % st[C.STATUS_NAN])
+    if st[C.STATUS_BIN_RANGE]:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d (%d view scores)"
+                         % (num_group, num_group, st[C.STATUS_BIN_RANGE]))
+    if st[C.STATUS_BAD_SCHEME]:
+        raise ValueError("group_scheme columns must be one-hot: every view in exactly one group "
+                         "(%d columns are not)" % st[C.STATUS_BAD_SCHEME])
+
+
+class ScoreResult:
+    """x (raw FC output), scores, bins, per-view flags and the status words."""
+    __slots__ = ("x", "scores", "bins", "flags", "status", "num_group")
+
+    def __init__(self, x, scores, bins, flags, status, num_group):
+        self.x, self.scores, self.bins, self.flags, self.status = x, scores, bins, flags, status
+        self.num_group = num_group
+
+    def check(self):
+        raise_for_status(self.status, self.num_group)
+        return self
+
+    def near_edge(self):
+        """bool tensor: views whose score is within edge_ulps of a bin edge."""
+        return (self.flags & C.FLAG_NEAR_EDGE) != 0
+
+
+# --------------------------------------------------------------------------
+# score + bin                                           nets/model.py:143-148, :23
+# --------------------------------------------------------------------------
+def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulps=1, clamp=False,
+              check=True, process_group=None) -> ScoreResult:
+    """Per-view discrimination score and bin.
+
+    R: raw view descriptors after GAP (nets/model.py:144), [B, V, C] ('bvd'),
+       [V, B, C] ('vbd') or a list of V [B, C] tensors; float32 or bfloat16.
+    W [V, C], b [V]: the V separate Dense(1) layers (nets/model.py:145), float32.
+    score_reduce 'shape': one score per (shape, view), bins [B, V] - the
+       reference at batch size 1 per shape.  'batch': the literal
+       tf.reduce_mean over the batch (nets/model.py:146), bins [1, V]; with a
+       torch.distributed ``process_group`` the per-view sums are all-reduced
+       first so every rank bins the same global-batch mean.
+    """
+    rv = _Views(R, layout, "R")
+    _require_cuda(W, "W"), _require_cuda(b, "b")
+    if W.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError("W and b must be float32")
+    Wc, bc = W.contiguous(), b.contiguous()
+    if tuple(Wc.shape) != (rv.V, rv.D) or tuple(bc.shape) != (rv.V,):
+        raise ValueError("W must be [V, C] = %s and b [V], got %s and %s"
+                         % ((rv.V, rv.D), tuple(Wc.shape), tuple(bc.shape)))
+    dev = rv.device
+    L = C.lib()
+    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    dt = _dtype_code(rv.dtype)
+    with torch.cuda.device(dev):
+        if score_reduce == "shape":
+            x = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
+            scores = torch.empty_like(x)
+            bins = torch.empty((rv.B, rv.V), dtype=torch.int32, device=dev)
+            flags = torch.empty_like(bins)
+            C.check(L.gvcnn_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(x), _ptr(scores), _ptr(bins),
+                                          _ptr(flags), _ptr(status), rv.B, rv.V, rv.D, num_group,
+                                          rv.layout, dt, edge_ulps, int(clamp), _stream()),
+                    "gvcnn_score_bin_fwd")
+        elif score_reduce == "batch":
+            xb = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
+            C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb), rv.B, rv.V, rv.D,
+                                           rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
+            xsum = torch.empty((1, rv.V), dtype=torch.float32, device=dev)
+            C.check(L.gvcnn_batch_sum_x(_ptr(xb), _ptr(xsum), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
+            denom = rv.B
+            if process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(xsum, group=process_group)
+                cnt = torch.tensor([rv.B], dtype=torch.int64, device=dev)
+                dist.all_reduce(cnt, group=process_group)
+                denom = int(cnt.item())
+            x = xsum
+            scores = torch.empty_like(x)
+            bins = torch.empty((1, rv.V), dtype=torch.int32, device=dev)
+            flags = torch.empty_like(bins)
+            C.check(L.gvcnn_score_bin(_ptr(x), ctypes.c_float(float(denom)), _ptr(scores), _ptr(bins),
+                                      _ptr(flags), _ptr(status), rv.V, num_group, edge_ulps, int(clamp),
+                                      _stream()), "gvcnn_score_bin")
+            x = x / float(denom)
+        else:
+            raise ValueError("score_reduce must be 'shape' or 'batch'")
+    res = ScoreResult(x, scores, bins, flags, status, num_group)
+    if check:
+        res.check()
+    return res
+
+
+def view_scores(raw_view_descriptors, W, b, score_reduce="batch", layout=None):
+    """view_discrimination_scores as nets/model.py:144-148 produces them:
+    sigmoid(log|mean_n(Dense(1)(raw))|) - [1, V] for the literal 'batch' mode,
+    [B, V] for 'shape'."""
+    return score_bin(raw_view_descriptors, W, b, 1, score_reduce=score_reduce, layout=layout,
+                     edge_ulps=0, clamp=True, check=False).scores
+
+
+# --------------------------------------------------------------------------
+# group_scheme / group_weight                           nets/model.py:16-41
+# --------------------------------------------------------------------------
+def _bins_from_scores(scores2d: torch.Tensor, num_group: int, clamp=False, check=True):
+    L = C.lib()
+    dev = scores2d.device
+    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    bins = torch.empty(scores2d.shape, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(L.gvcnn_bins_from_scores(_ptr(scores2d), _ptr(bins), None, _ptr(status), scores2d.numel(),
+                                         num_group, 0, int(clamp), _stream()), "gvcnn_bins_from_scores")
+    if check:
+        raise_for_status(status, num_group)
+    return bins
+
+
+def group_scheme(view_discrimination_score, num_group, num_views):
+    """One-hot grouping scheme.  Mirrors nets/model.py:16-25.
+
+    view_discrimination_score: what the reference passes - a sequence holding
+    ONE sequence of V scores (train.py:270-277, hence the ``[0]``), or a CUDA
+    tensor [1, V]; a CUDA tensor [B, V] with B > 1 gives per-shape schemes
+    [B, num_group, V].  Returns an int32 CUDA tensor [num_group, num_views].
+    Raises IndexError when a score maps to bin >= num_group (score == 1.0) and
+    ValueError on NaN, like the reference.  The reference's hard-coded ``* 10``
+    (model.py:23) is generalised to ``* num_group`` (identical at 10).
+    """
+    s = view_discrimination_score
+    if isinstance(s, torch.Tensor):
+        _require_cuda(s, "view_discrimination_score")
+        s2 = s.to(torch.float32).reshape(-1, s.shape[-1]).contiguous()
+    else:
+        row = s[0]
+        if isinstance(row, torch.Tensor):
+            _require_cuda(row, "view_discrimination_score")
+            s2 = row.to(torch.float32).reshape(1, -1).contiguous()
+        else:
+            items = [t for t in row]
+            if len(items) and isinstance(items[0], torch.Tensor):
+                s2 = torch.stack([t.reshape(()) for t in items]).to(torch.float32).reshape(1, -1)
+                _require_cuda(s2, "view_discrimination_score")
+            else:
+                if not torch.cuda.is_available():
+                    raise RuntimeError("gvcnn_b200 needs a CUDA device: there is no CPU path")
+                s2 = torch.tensor([float(t) for t in items], dtype=torch.float32, device="cuda").reshape(1, -1)
+    if s2.shape[1] != num_views:
+        raise ValueError("expected %d view scores, got %d" % (num_views, s2.shape[1]))
+    bins = _bins_from_scores(s2, num_group)
+    rows = bins.shape[0]
+    scheme = torch.empty((rows, num_group, num_views), dtype=torch.int32, device=bins.device)
+    with torch.cuda.device(bins.device):
+        C.check(C.lib().gvcnn_bins_to_scheme(_ptr(bins), _ptr(scheme), rows, num_views, num_group, _stream()),
+                "gvcnn_bins_to_scheme")
+    return scheme[0] if rows == 1 else scheme
+
+
+def _scheme_to_bins(g_schemes: torch.Tensor, check=True):
+    _require_cuda(g_schemes, "group_scheme")
+    sc = g_schemes.to(torch.int32)
+    if sc.dim() == 2:
+        sc = sc[None]
+    sc = sc.contiguous()
+    rows, G, V = sc.shape
+    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=sc.device)
+    bins = torch.empty((rows, V), dtype=torch.int32, device=sc.device)
+    with torch.cuda.device(sc.device):
+        C.check(C.lib().gvcnn_scheme_to_bins(_ptr(sc), _ptr(bins), _ptr(status), rows, V, G, _stream()),
+                "gvcnn_scheme_to_bins")
+    if check:
+        raise_for_status(status, G)
+    return bins, G
+
+
+def group_weight(g_schemes):
+    """weights[g] = 1 + number of views in group g.  Mirrors nets/model.py:28-41.
+    g_schemes: int CUDA tensor [G, V] (or [B, G, V]); returns float32 [G] (or [B, G])."""
+    bins, G = _scheme_to_bins(g_schemes)
+    rows, V = bins.shape
+    w = torch.empty((rows, G), dtype=torch.float32, device=bins.device)
+    with torch.cuda.device(bins.device):
+        C.check(C.lib().gvcnn_group_weight(_ptr(bins), _ptr(w), rows, V, G, _stream()), "gvcnn_group_weight")
+    return w[0] if g_schemes.dim() == 2 else w
+
+
+# --------------------------------------------------------------------------
+# pooling + fusion                                      nets/model.py:44-102
+# --------------------------------------------------------------------------
+def _pool_fuse_fwd(fv: _Views, bins: torch.Tensor, G: int, pool: str, empty_fill: float,
+                   weights: Optional[torch.Tensor], want_mask: bool, want_groups: bool):
+    dev = fv.device
+    dt = _dtype_code(fv.dtype)
+    bins = bins.to(torch.int32).contiguous()
+    if bins.dim() == 1:
+        bins = bins[None]
+    if bins.shape[-1] != fv.V or bins.shape[0] not in (1, fv.B):
+        raise ValueError("bins must be [V], [1, V] or [B, V] with V=%d, B=%d; got %s"
+                         % (fv.V, fv.B, tuple(bins.shape)))
+    bin_stride = fv.V if (bins.shape[0] == fv.B and fv.B > 1) else 0
+    w_ptr, w_stride = None, 0
+    if weights is not None:
+        _require_cuda(weights, "group_weight")
+        weights = weights.to(torch.float32).contiguous()
+        if weights.dim() == 1:
+            weights = weights[None]
+        if weights.shape[-1] != G or weights.shape[0] not in (1, fv.B):
+            raise ValueError("group_weight must be [G] or [B, G]")
+        w_ptr, w_stride = _ptr(weights), (G if (weights.shape[0] == fv.B and fv.B > 1) else 0)
+    S = torch.empty((fv.B, fv.D), dtype=fv.dtype, device=dev)
+    mask = None
+    if want_mask and pool == "max":
+        mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
+    P = torch.empty((G, fv.B, fv.D), dtype=fv.dtype, device=dev) if want_groups else None
+    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().gvcnn_pool_fuse_fwd(fv.arg, _ptr(bins), bin_stride, w_ptr, w_stride, _ptr(S), _ptr(P),
+                                            _ptr(mask), _ptr(status), fv.B, fv.V, fv.D, G, _POOL[pool],
+                                            ctypes.c_float(empty_fill), fv.layout, dt, _stream()),
+                "gvcnn_pool_fuse_fwd")
+    return S, mask, P, status, bins, bin_stride, weights, w_stride
+
+
+def _pool_fuse_bwd(dS: torch.Tensor, fv_like: _Views, bins, bin_stride, weights, w_stride, mask, G, pool):
+    dS = dS.contiguous()
+    out, gv = fv_like.empty_like()
+    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dS.device)
+    with torch.cuda.device(dS.device):
+        C.check(C.lib().gvcnn_pool_fuse_bwd(_ptr(dS), _ptr(bins), bin_stride, _ptr(weights), w_stride,
+                                            _ptr(mask), gv.arg, _ptr(status), gv.B, gv.V, gv.D, G,
+                                            _POOL[pool], gv.layout, _dtype_code(gv.dtype), _stream()),
+                "gvcnn_pool_fuse_bwd")
+    return out
+
+
+class _PoolFuseFn(torch.autograd.Function):
+    """S = fused view_pooling + group_fusion; backward = TF autodiff of
+    nets/model.py:62-100 (dF only: no gradient reaches scores / weights,
+    train.py:127-128, utils/train_utils.py:203-206)."""
+
+    @staticmethod
+    def forward(ctx, bins, weights, G, pool, empty_fill, layout, n_views, *views):
+        is_list = layout == "list"
+        fv = _Views(list(views) if is_list else views[0], None if is_list else layout, "F")
+        need_grad = any(v.requires_grad for v in views)
+        S, mask, _, status, bins_c, bstride, w_c, wstride = _pool_fuse_fwd(
+            fv, bins, G, pool, empty_fill, weights, want_mask=need_grad, want_groups=False)
+        ctx.fv, ctx.G, ctx.pool = fv, G, pool
+        ctx.bstride, ctx.wstride = bstride, wstride
+        ctx.save_for_backward(bins_c, mask if mask is not None else torch.empty(0, device=S.device),
+                              w_c if w_c is not None else torch.empty(0, device=S.device))
+        ctx.mark_non_differentiable(status)
+        return S.reshape(fv.view_shape), status
+
+    @staticmethod
+    def backward(ctx, dS, _dstatus):
+        bins_c, mask, w_c = ctx.saved_tensors
+        mask = mask if mask.numel() else None
+        w_c = w_c if w_c.numel() else None
+        fv = ctx.fv
+        out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins_c, ctx.bstride, w_c, ctx.wstride, mask,
+                             ctx.G, ctx.pool)
+        grads = tuple(out) if isinstance(out, list) else (out,)
+        return (None, None, None, None, None, None, None) + grads
+
+
+def pool_fuse(final_view_descriptors, bins, num_group, pool="max", empty_fill=1.0, layout=None,
+              group_weight=None, check=False):
+    """Fused view_pooling + group_fusion (nets/model.py:44-102) from a bin map.
+
+    final_view_descriptors: list of V tensors [N, ...] (the reference's layout),
+    or one tensor [B, V, ...] (layout='bvd') / [V, B, ...] (layout='vbd').
+    bins: int32 [B, V] (per-shape) or [V] / [1, V] (one scheme for the batch).
+    Returns the shape descriptor with the shape of one view, differentiable
+    w.r.t. the view descriptors.
+    """
+    if isinstance(final_view_descriptors, (list, tuple)):
+        views, lay = tuple(final_view_descriptors), "list"
+    else:
+        views, lay = (final_view_descriptors,), (layout or "bvd")
+    _require_cuda(bins, "bins")
+    S, status = _PoolFuseFn.apply(bins, group_weight, num_group, pool, empty_fill, lay, len(views), *views)
+    if check:
+        raise_for_status(status, num_group)
+    return S
+
+
+class GroupDescriptors(dict):
+    """What ``view_pooling`` returns: behaves like the reference's
+    ``{group index: pooled descriptor}`` dict (nets/model.py:61,72), but lazy -
+    the G pooled tensors are only materialised (one kernel writing [G, B, D])
+    if somebody indexes or iterates the dict.  ``group_fusion`` recognises this
+    object and runs the single-pass fused kernel on the original views."""
+
+    def __init__(self, views, layout, bins, num_group, pool, empty_fill):
+        super().__init__()
+        self._views, self._layout = views, layout
+        self._bins, self._G, self._pool, self._fill = bins, num_group, pool, empty_fill
+        self._done = False
+
+    def _materialise(self):
+        if self._done:
+            return
+        fv = _Views(list(self._views) if self._layout == "list" else self._views[0],
+                    None if self._layout == "list" else self._layout, "F")
+        _, _, P, _, _, _, _, _ = _pool_fuse_fwd(fv, self._bins, self._G, self._pool, self._fill, None,
+                                                want_mask=False, want_groups=True)
+        for g in range(self._G):
+            dict.__setitem__(self, g, P[g].reshape(fv.view_shape))
+        self._done = True
+
+    def __getitem__(self, k):
+        self._materialise()
+        return dict.__getitem__(self, k)
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        return self._G
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+
+def view_pooling(final_view_descriptors, group_scheme, pool="max", empty_fill=1.0, layout=None):
+    """Intra-group view pooling.  Mirrors nets/model.py:44-74.
+
+    final_view_descriptors: list of V CUDA tensors [N, h, w, C] (as in the
+    reference), or a stacked tensor with ``layout``.  group_scheme: int tensor
+    [num_group, num_view] (one scheme for the batch, as in the reference) or
+    [B, num_group, num_view].  pool='max', empty_fill=1.0 is the shipped
+    model.py behaviour (:63,:72); pool='mean', empty_fill=0.0 is unit_test.py's.
+    Returns a GroupDescriptors dict {g: pooled descriptor}.
+    """
+    bins, G = _scheme_to_bins(group_scheme)
+    if isinstance(final_view_descriptors, (list, tuple)):
+        views, lay = tuple(final_view_descriptors), "list"
+    else:
+        views, lay = (final_view_descriptors,), (layout or "bvd")
+    return GroupDescriptors(views, lay, bins, G, pool, empty_fill)
+
+
+def group_fusion(group_descriptors, group_weight):
+    """Shape descriptor = sum_g w_g * P_g / sum_g w_g.  Mirrors nets/model.py:77-102.
+
+    With the GroupDescriptors returned by ``view_pooling`` this runs the fused
+    single-pass kernel over the original views (and is differentiable w.r.t.
+    them).  ``group_weight`` is honoured as given ([G] or [B, G] float32), so
+    weights other than ``model.group_weight``'s 1 + count also work.
+    """
+    if not isinstance(group_descriptors, GroupDescriptors):
+        raise TypeError("group_fusion expects the GroupDescriptors returned by view_pooling")
+    gd = group_descriptors
+    _require_cuda(group_weight, "group_weight")
+    S, _ = _PoolFuseFn.apply(gd._bins, group_weight, gd._G, gd._pool, gd._fill, gd._layout,
+                             len(gd._views), *gd._views)
+    return S
+
+
+def basic_pool(final_view_descriptors, layout=None):
+    """``tf.reduce_max(final_view_descriptors, axis=0)`` - the MVCNN-style
+    verification path (nets/model.py:202, :160-161) = all views in one group,
+    unit weight."""
+    fv = _Views(final_view_descriptors, layout, "F")
+    bins = torch.zeros((1, fv.V), dtype=torch.int32, device=fv.device)
+    w = torch.ones((1, 1), dtype=torch.float32, device=fv.device)
+    return pool_fuse(final_view_descriptors, bins, 1, pool="max", empty_fill=0.0, layout=layout,
+                     group_weight=w)
+
+
+def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max",
+                    empty_fill=1.0, score_reduce="shape", layout=None, clamp=False, check=True,
+                    process_group=None, edge_ulps=1):
+    """The whole hot path in two launches, no host hop (replaces the
+    partial_run split of train.py:264-288): score + bin, then pool + fuse.
+    Returns (shape_descriptor, ScoreResult)."""
+    sr = score_bin(raw_view_descriptors, W, b, num_group, score_reduce=score_reduce, layout=layout,
+                   edge_ulps=edge_ulps, clamp=clamp, check=check, process_group=process_group)
+    S = pool_fuse(final_view_descriptors, sr.bins, num_group, pool=pool, empty_fill=empty_fill, layout=layout)
+    return S, sr
+
+
+class GVCNNHead(torch.nn.Module):
+    """The trainable state of the path: V separate Dense(1) score layers
+    (Keras defaults: glorot-uniform kernel, zero bias; nets/model.py:145 sits
+    inside the view loop) and the classifier Dense(num_classes) after global
+    average pooling (nets/model.py:163-164)."""
+
+    def __init__(self, num_views, raw_channels, final_channels, num_classes, num_group=10, pool="max",
+                 empty_fill=1.0, score_reduce="batch"):
+        super().__init__()
+        self.num_views, self.num_group = num_views, num_group
+        self.pool, self.empty_fill, self.score_reduce = pool, empty_fill, score_reduce
+        lim = math.sqrt(6.0 / (raw_channels + 1))
+        self.score_kernel = torch.nn.Parameter(torch.empty(num_views, raw_channels).uniform_(-lim, lim))
+        self.score_bias = torch.nn.Parameter(torch.zeros(num_views))
+        self.classifier = torch.nn.Linear(final_channels, num_classes)
+        lim2 = math.sqrt(6.0 / (final_channels + num_classes))
+        torch.nn.init.uniform_(self.classifier.weight, -lim2, lim2)
+        torch.nn.init.zeros_(self.classifier.bias)
+
+    def forward(self, raw_view_descriptors, final_view_descriptors, process_group=None, check=True):
+        """raw: post-GAP block3 features [N, V, C_raw] (or list of V [N, C_raw]);
+        final: list of V [N, h, w, C] maps or [N, V, h, w, C].  Returns
+        (view_discrimination_scores, shape_descriptor, logits) like
+        nets/model.py:166."""
+        S, sr = grouping_fusion(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
+                                final_view_descriptors, self.num_group, pool=self.pool,
+                                empty_fill=self.empty_fill, score_reduce=self.score_reduce,
+                                process_group=process_group, check=check)
+        net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
+        logits = self.classifier(net.to(self.classifier.weight.dtype))
+        return sr.scores, S, logits
+
+
+def gvcnn_head(raw_view_descriptors, final_view_descriptors, head: GVCNNHead, group_scheme=None,
+               group_weight=None):
+    """nets/model.py:143-166 from the backbone outputs on: with ``group_scheme``
+    / ``group_weight`` given (the reference's placeholders, train.py:127-128) it
+    pools and fuses with them; without, it computes them on the device."""
+    if group_scheme is None:
+        return head(raw_view_descriptors, final_view_descriptors)
+    scores = view_scores(raw_view_descriptors, head.score_kernel.detach(), head.score_bias.detach(),
+                         score_reduce=head.score_reduce)
+    desc = view_pooling(final_view_descriptors, group_scheme, pool=head.pool, empty_fill=head.empty_fill)
+    w = group_weight if group_weight is not None else globals()["group_weight"](group_scheme)
+    S = group_fusion(desc, w)
+    net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
+    return scores, S, head.classifier(net.to(head.classifier.weight.dtype))

@@ -1,0 +1,208 @@
+/*
+ * gvcnn_b200.h - C ABI of libgvcnn_sm100.so: the GVCNN view-grouping + fusion
+ * hot path as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (ace19-dev/gvcnn-tf) is pure Python over TensorFlow 1.x; it has
+ * no FFI of its own.  Each entry point below replaces the reference interface
+ * cited beside it; the ctypes binding a maintainer of the reference would add
+ * is shown in INTEGRATION.md and implemented in gvcnn-tf_b200/_cabi.py.
+ *
+ * Conventions (all entry points):
+ *   - every tensor pointer is a DEVICE pointer owned by the caller unless the
+ *     name says `host`; the library allocates nothing persistent and keeps no
+ *     global state; calls are stream-ordered, asynchronous and re-entrant;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 = ok, < 0 = GVCNN_E_* argument error (nothing was
+ *     launched), > 0 = a cudaError_t from the launch;  nothing throws;
+ *   - there is no CPU path: a machine without an sm_100 device gets
+ *     GVCNN_E_NO_DEVICE / a CUDA error, never a silent fallback;
+ *   - data-dependent errors the reference raises as Python exceptions
+ *     (IndexError for score == 1.0 -> bin == num_group, ValueError for a NaN
+ *     score; nets/model.py:23) are counted into `status` (device int32[4],
+ *     GVCNN_STATUS_*), which the caller zeroes and reads back when it wants
+ *     the reference's error behaviour.
+ */
+#ifndef GVCNN_B200_H_
+#define GVCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVCNN_ABI_VERSION 1
+#define GVCNN_MAX_VIEWS 128      /* V: 6..80 in the reference's sweeps           */
+#define GVCNN_MAX_GROUPS 4096    /* num_group; the reference only ever uses 10   */
+
+/* dtype of R / F / S / dS / dF.  Arithmetic is always float32. */
+#define GVCNN_F32 0
+#define GVCNN_BF16 1
+
+/* layout of a per-view tensor X (R, F or dF)
+ *   BVD : one array [B, V, D]     (north_star's shape-major layout)
+ *   VBD : one array [V, B, D]     (tf.stack of the reference's view list,
+ *                                  nets/model.py:63,69)
+ *   PTRS: V separately allocated [B, D] arrays - the reference's Python list
+ *         of per-view tensors (nets/model.py:149); pass a HOST array of V
+ *         device pointers. */
+#define GVCNN_LAYOUT_BVD 0
+#define GVCNN_LAYOUT_VBD 1
+#define GVCNN_LAYOUT_PTRS 2
+
+#define GVCNN_POOL_MAX 0         /* tf.reduce_max, nets/model.py:72 (shipped)    */
+#define GVCNN_POOL_MEAN 1        /* tf.reduce_mean, unit_test.py:31              */
+
+/* status words */
+#define GVCNN_STATUS_WORDS 4
+#define GVCNN_STATUS_BIN_RANGE 0 /* # bins outside [0,G): reference IndexError   */
+#define GVCNN_STATUS_NAN 1       /* # NaN scores: reference ValueError           */
+#define GVCNN_STATUS_NEAR_EDGE 2 /* # scores within edge_ulps of a bin edge      */
+#define GVCNN_STATUS_BAD_SCHEME 3 /* # scheme columns that are not one-hot          */
+
+/* per-view flag bits written to `flags` */
+#define GVCNN_FLAG_NEAR_EDGE 1
+#define GVCNN_FLAG_BIN_RANGE 2
+#define GVCNN_FLAG_NAN 4
+
+/* argument errors */
+#define GVCNN_E_BAD_ARG (-1)     /* null pointer, non-positive dimension         */
+#define GVCNN_E_BAD_DTYPE (-2)
+#define GVCNN_E_BAD_LAYOUT (-3)
+#define GVCNN_E_TOO_MANY_VIEWS (-4)
+#define GVCNN_E_TOO_MANY_GROUPS (-5)
+#define GVCNN_E_MISALIGNED (-6)  /* a pointer not aligned to its element size    */
+#define GVCNN_E_NO_DEVICE (-7)   /* no CUDA device / not compute capability 10.x */
+#define GVCNN_E_BAD_MODE (-8)
+#define GVCNN_E_WORKSPACE (-9)   /* workspace too small                          */
+
+int gvcnn_version(void);
+const char *gvcnn_strerror(int code);
+/* 0 if the current device can run this library (compute capability 10.x). */
+int gvcnn_check_device(void);
+
+/* --- score --------------------------------------------------------------
+ * Replaces the per-view `GlobalAveragePooling2D -> Dense(1)` of
+ * nets/model.py:144-145 (V separate FC layers: W [V, C] float32, bias [V]).
+ * x[b, v] = sum_c R[b, v, c] * W[v, c] + bias[v], one warp per (shape, view)
+ * row, fixed summation order (see DESIGN.md "score kernel").
+ * R: [B,V,C] / [V,B,C] / V pointers (r_layout), dtype f32 or bf16.
+ * x: float32 [B, V]. */
+int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x,
+                         int B, int V, int C, int r_layout, int dtype, void *stream);
+
+/* Deterministic column sums xsum[v] = sum_b x[b, v] (float32 [V]) for the
+ * literal `tf.reduce_mean(raw)` over the batch at nets/model.py:146.  Kept
+ * separate from the division so a multi-GPU caller can all-reduce xsum first
+ * (SURVEY.md 8e). */
+int gvcnn_batch_sum_x(const float *x, float *xsum, int B, int V, void *stream);
+
+/* Element-wise tail of the score path for n values:
+ *   xm = x / denom            (denom = 1 per-shape, = global batch size after
+ *                              gvcnn_batch_sum_x;  nets/model.py:146)
+ *   s  = |xm| / (1 + |xm|)    == sigmoid(log|xm|), nets/model.py:147
+ *   bin = (int)(s * (float)G) float32 multiply, truncation; nets/model.py:23
+ * Replaces model.group_scheme (nets/model.py:16-25; train.py:277) - the
+ * one-hot [G, V] scheme is the dense form of `bins`.
+ * flags (nullable) gets GVCNN_FLAG_* per element; status counts them.
+ * clamp != 0 stores min(bin, G-1) instead of the out-of-range value (the
+ * flag / status are still raised). */
+int gvcnn_score_bin(const float *x, float denom, float *scores, int32_t *bins,
+                    int32_t *flags, int32_t *status, int64_t n, int G,
+                    int edge_ulps, int clamp, void *stream);
+
+/* gvcnn_view_score_fwd + gvcnn_score_bin(denom = 1) in ONE kernel: the
+ * per-shape path (SURVEY.md D5 'shape').  Replaces the device->host->device
+ * hop of train.py:270-288.  x (nullable), scores, bins: [B, V]. */
+int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias,
+                        float *x, float *scores, int32_t *bins, int32_t *flags,
+                        int32_t *status, int B, int V, int C, int G,
+                        int r_layout, int dtype, int edge_ulps, int clamp, void *stream);
+
+/* --- scheme / weight glue (the reference's host NumPy part) -----------------
+ * gvcnn_bins_from_scores: model.group_scheme's arithmetic on already-computed
+ *   scores (nets/model.py:23): bin = (int)(float32(s) * float32(G)); same
+ *   flags / status / clamp behaviour as gvcnn_score_bin.
+ * gvcnn_bins_to_scheme: dense one-hot int32 [rows, G, V] exactly as
+ *   model.group_scheme returns it (nets/model.py:21-23) from bins [rows, V].
+ * gvcnn_scheme_to_bins: the inverse, for callers that hand view_pooling a
+ *   scheme matrix (nets/model.py:44); columns that are not one-hot are counted
+ *   in status[GVCNN_STATUS_BAD_SCHEME] (the kernels need every view in exactly
+ *   one group, which group_scheme guarantees) and mapped to bin 0.
+ * gvcnn_group_weight: model.group_weight (nets/model.py:28-41):
+ *   weights[row, g] = 1 + #{v : bins[row, v] == g}, float32 [rows, G]. */
+int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, int32_t *status,
+                           int64_t n, int G, int edge_ulps, int clamp, void *stream);
+int gvcnn_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, void *stream);
+int gvcnn_scheme_to_bins(const int32_t *scheme, int32_t *bins, int32_t *status, int rows, int V, int G,
+                         void *stream);
+int gvcnn_group_weight(const int32_t *bins, float *weights, int rows, int V, int G, void *stream);
+
+/* --- pooling + fusion ------------------------------------------------------
+ * Replaces model.group_weight (nets/model.py:28-41), model.view_pooling
+ * (:44-74) and model.group_fusion (:77-102) in one pass over F:
+ *   w_g = 1 + n_g ;  P_g = max|mean over the group's views, or `empty_fill`
+ *   for an empty group ;  S = (sum_g w_g * P_g, g ascending) / (G + V).
+ * F: per-view descriptors (f_layout, dtype); for PTRS pass the host pointer
+ *    array as F.  D = everything after the view axis, flattened (h*w*C).
+ * bins: int32, element (b, v) at bins[b * bin_stride_b + v]; bin_stride_b = V
+ *    for per-shape maps, 0 for one scheme shared by the batch (literal mode).
+ * weights (nullable): float32 group weights, element (b, g) at
+ *    weights[b * weight_stride_b + g] (stride 0 = shared) - the second argument
+ *    of model.group_fusion (nets/model.py:77).  Null = the reference's own
+ *    group_weight, 1 + n_g, computed in-kernel from the bins.
+ * S: [B, D] in `dtype`.
+ * group_desc (nullable): the G group descriptors P_g as [G, B, D] in `dtype` -
+ *    what model.view_pooling returns as a dict (nets/model.py:72); only for
+ *    callers that index the dict, the fused path never materialises it.
+ * tie_mask (nullable): routing aid for the max-mode backward, uint8
+ *    [ceil(V/8), B, D]; bit k%8 of plane k/8 <=> the k-th view in (bin, view)
+ *    order attains its group's maximum.  Opaque to callers.
+ * status (nullable): bins outside [0, G) are counted in
+ *    status[GVCNN_STATUS_BIN_RANGE] and clamped for memory safety. */
+int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b,
+                        const float *weights, int64_t weight_stride_b,
+                        void *S, void *group_desc, uint8_t *tie_mask, int32_t *status,
+                        int B, int V, int64_t D, int G, int pool, float empty_fill,
+                        int f_layout, int dtype, void *stream);
+
+/* Backward of the above (TF autodiff of nets/model.py:62-100):
+ *   dF_v = (1/num_selected | 0) * (w_g * (dS / (G+V)))     max  (ties share)
+ *   dF_v = (w_g * (dS / (G+V))) / n_g                      mean
+ * dS [B, D]; dF in g_layout (PTRS: host array of V device pointers).
+ * tie_mask is required for GVCNN_POOL_MAX. */
+int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_b,
+                        const float *weights, int64_t weight_stride_b,
+                        const uint8_t *tie_mask, void *dF, int32_t *status,
+                        int B, int V, int64_t D, int G, int pool,
+                        int g_layout, int dtype, void *stream);
+
+/* Which pooling kernel variant the next calls use: 0 = auto, 1 = bulk-copy
+ * (TMA, cp.async.bulk) staged, 2 = plain vector loads staged through shared
+ * memory.  Process-wide, for A/B measurement only. */
+int gvcnn_set_pool_variant(int variant);
+
+/* --- host-buffer path (end-to-end) ---------------------------------------
+ * One call = what one `sess.partial_run` pair does for this path in
+ * train.py:270-288, with HOST (preferably pinned) buffers: copies R and F to
+ * the device in chunks of shapes, runs score+bin and pool+fuse, copies S (and
+ * scores / bins if non-null) back, overlapping copies with kernels on two
+ * streams.  BVD layout.  d_workspace is caller-owned device memory of at
+ * least gvcnn_host_workspace_bytes(...) bytes.  Synchronous: returns when the
+ * outputs are in host memory.  If dS_host / dF_host are non-null it also runs
+ * the backward and returns dF. */
+size_t gvcnn_host_workspace_bytes(int chunk_shapes, int V, int C, int64_t D, int dtype, int training);
+int gvcnn_grouping_fusion_host(const void *R_host, const void *F_host,
+                               const float *W_dev, const float *bias_dev,
+                               void *S_host, float *scores_host, int32_t *bins_host,
+                               const void *dS_host, void *dF_host,
+                               int32_t *status_host,
+                               int B, int V, int C, int64_t D, int G, int pool, float empty_fill,
+                               int dtype, int chunk_shapes,
+                               void *d_workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVCNN_B200_H_ */
