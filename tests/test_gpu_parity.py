@@ -1,0 +1,404 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via gvcnn_tf_b200.model) against the
+oracle on identical seeded inputs.  Run on the B200 box with ``pytest -m gpu``.
+
+Bars (BASELINE.json north_star):
+  * group indices bit-exact; scores within `edge_ulps` of a bin edge reported separately;
+  * float32 descriptors and gradients: the kernels follow the oracle's op order with one
+    rounding per op, so the tests demand BIT-EXACT equality (stricter than the 1e-5 relative
+    the north star asks for); bf16: 1e-2 relative (and in fact exact after rounding).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gvcnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5     # north_star tolerance (fp32); the assertions below are exact, this is the fallback bar
+RTOL_BF16 = 1e-2    # north_star tolerance (bf16)
+
+
+@pytest.fixture(scope="module")
+def model():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gvcnn_tf_b200 import model as m, _cabi
+    assert _cabi.lib().gvcnn_check_device() == 0, "libgvcnn_sm100.so needs a compute-capability 10.x device"
+    return m
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def make_inputs(seed, B, V, D, G, ties=False):
+    rng = np.random.default_rng(seed)
+    F = rng.standard_normal((B, V, D)).astype(np.float32)
+    if ties:
+        F = np.maximum(np.round(F * 2) / 2, 0).astype(np.float32)
+    bins = rng.integers(0, G, (B, V)).astype(np.int32)
+    dS = rng.standard_normal((B, D)).astype(np.float32)
+    return F, bins, dS
+
+
+# ---------------------------------------------------------------- KATs / golden
+def test_kat2_through_reference_signatures(model, golden_dir):
+    with open(os.path.join(golden_dir, "kat.json")) as f:
+        kat = json.load(f)
+    F = np.array(kat["F"], dtype=np.float32)
+    views = [dev(f[None]) for f in F]                       # V tensors [N=1, 4]
+    scheme = dev(np.array(kat["scheme"], dtype=np.int32))
+    w = model.group_weight(scheme)
+    assert w.cpu().tolist() == kat["kat2_weights"]
+    desc = model.view_pooling(views, scheme)
+    S = model.group_fusion(desc, w)
+    np.testing.assert_array_equal(S.cpu().numpy()[0], np.array(kat["kat2_S"], dtype=np.float32))
+    for g, want in kat["kat2_max_ones_groups"].items():
+        assert desc[int(g)].cpu().numpy()[0].tolist() == want
+    # KAT-1: the unit_test.py variant (mean, zeros)
+    desc1 = model.view_pooling(views, scheme, pool="mean", empty_fill=0.0)
+    np.testing.assert_allclose(desc1[3].cpu().numpy()[0], kat["kat1_mean_zeros_float_g3"], rtol=1e-6)
+    assert desc1[2].cpu().numpy()[0].tolist() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("case", ["kat2", "rand_v6", "rand_v12", "tie_v12", "rand_v20"])
+def test_reference_graph_vectors(model, golden_dir, case):
+    z = np.load(os.path.join(golden_dir, "ref_graph_pool_fuse.npz"))
+    F, scheme, w, S, P = (z["%s__%s" % (case, k)] for k in ("F", "scheme", "w", "S", "P"))
+    views = [dev(F[v]) for v in range(F.shape[0])]
+    sch = dev(scheme.astype(np.int32))
+    wd = model.group_weight(sch)
+    np.testing.assert_array_equal(wd.cpu().numpy(), w)
+    desc = model.view_pooling(views, sch)
+    np.testing.assert_array_equal(model.group_fusion(desc, wd).cpu().numpy(), S)
+    for g in range(scheme.shape[0]):
+        np.testing.assert_array_equal(desc[g].cpu().numpy(), P[g])
+
+
+def test_reference_host_vectors(model, golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_graph_host.npz"))
+    for i in range(int(z["n"])):
+        sc = z["scores_%d" % i]
+        scheme = model.group_scheme([[float(s) for s in sc]], 10, len(sc))
+        np.testing.assert_array_equal(scheme.cpu().numpy(), z["scheme_%d" % i])
+        np.testing.assert_array_equal(model.group_weight(scheme).cpu().numpy(), z["weight_%d" % i])
+        scheme2 = model.group_scheme(dev(sc[None]), 10, len(sc))
+        np.testing.assert_array_equal(scheme2.cpu().numpy(), z["scheme_%d" % i])
+
+
+def test_reference_error_behaviour(model):
+    with pytest.raises(IndexError):
+        model.group_scheme([[1.0, 0.3]], 10, 2)             # score == 1.0 -> bin 10 of 10
+    with pytest.raises(ValueError):
+        model.group_scheme([[float("nan"), 0.3]], 10, 2)
+    with pytest.raises(ValueError):                         # not one-hot
+        model.group_weight(dev(np.array([[1, 1], [1, 0]], dtype=np.int32)))
+    with pytest.raises(RuntimeError):                       # no CPU path
+        model.pool_fuse(torch.zeros(2, 3, 4), torch.zeros(2, 3, dtype=torch.int32), 4)
+    # |x| >= 2**24 -> score == 1.0 -> IndexError from the fused path too; clamp=True keeps going
+    R = dev(np.full((1, 2, 8), 2.0 ** 22, dtype=np.float32))
+    W = dev(np.ones((2, 8), dtype=np.float32))
+    b = dev(np.zeros(2, dtype=np.float32))
+    with pytest.raises(IndexError):
+        model.score_bin(R, W, b, 10)
+    sr = model.score_bin(R, W, b, 10, clamp=True, check=False)
+    assert sr.bins.cpu().tolist() == [[9, 9]] and int(sr.status[0]) == 2
+    Rn = R.clone()
+    Rn[0, 0, 0] = float("nan")
+    with pytest.raises(ValueError):
+        model.score_bin(Rn, W, b, 10)
+
+
+# ---------------------------------------------------------------- pooling + fusion
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0), ("max", 0.0), ("mean", 1.0)])
+@pytest.mark.parametrize("B,V,D,G", [
+    (33, 12, 2048, 8), (7, 6, 1024, 10), (5, 20, 1024, 16), (3, 80, 1024, 4), (9, 12, 2052, 2),
+    (4, 12, 100, 8), (2, 1, 64, 1), (3, 5, 7, 5), (1, 12, 4, 8), (2, 33, 260, 7),
+])
+def test_pool_fuse_fwd_bwd_bit_exact_f32(model, pool, fill, B, V, D, G):
+    F, bins, dS = make_inputs(B * 1000 + V * 10 + G, B, V, D, G, ties=(D % 2 == 0))
+    Ft = dev(F).requires_grad_(True)
+    S = model.pool_fuse(Ft, dev(bins), G, pool=pool, empty_fill=fill, check=True)
+    want = O.pool_fuse_fwd(F, bins, G, pool, fill)
+    np.testing.assert_array_equal(S.detach().cpu().numpy(), want)
+    S.backward(dev(dS))
+    np.testing.assert_array_equal(Ft.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("pool", ["max", "mean"])
+def test_pool_variants_agree(model, variant, pool):
+    """bulk-copy (TMA) staging and plain-load staging are the same function."""
+    from gvcnn_tf_b200 import _cabi
+    F, bins, dS = make_inputs(77, 19, 12, 2048, 8, ties=True)
+    try:
+        assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
+        S = model.pool_fuse(dev(F), dev(bins), 8, pool=pool)
+    finally:
+        _cabi.lib().gvcnn_set_pool_variant(0)
+    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, bins, 8, pool, 1.0))
+
+
+@pytest.mark.parametrize("layout", ["bvd", "vbd", "list"])
+@pytest.mark.parametrize("pool", ["max", "mean"])
+def test_layouts_and_spatial_maps(model, layout, pool):
+    """[B,V,...], [V,B,...] and the reference's list of V [N,h,w,C] maps; D = h*w*C."""
+    B, V, G, shape = 3, 6, 10, (5, 5, 64)
+    rng = np.random.default_rng(5)
+    F = np.maximum(rng.standard_normal((B, V) + shape), -0.5).astype(np.float32)
+    bins = rng.integers(0, G, (B, V)).astype(np.int32)
+    dS = rng.standard_normal((B,) + shape).astype(np.float32)
+    want = O.pool_fuse_fwd(F.reshape(B, V, -1), bins, G, pool, 1.0).reshape((B,) + shape)
+    wantg = O.pool_fuse_bwd(dS.reshape(B, -1), F.reshape(B, V, -1), bins, G, pool).reshape(F.shape)
+    if layout == "bvd":
+        x = dev(F).requires_grad_(True)
+        S = model.pool_fuse(x, dev(bins), G, pool=pool, layout="bvd")
+        S.backward(dev(dS))
+        g = x.grad.cpu().numpy()
+    elif layout == "vbd":
+        x = dev(F.transpose(1, 0, 2, 3, 4)).requires_grad_(True)
+        S = model.pool_fuse(x, dev(bins), G, pool=pool, layout="vbd")
+        S.backward(dev(dS))
+        g = x.grad.cpu().numpy().transpose(1, 0, 2, 3, 4)
+    else:
+        xs = [dev(F[:, v]).requires_grad_(True) for v in range(V)]
+        S = model.pool_fuse(xs, dev(bins), G, pool=pool)
+        S.backward(dev(dS))
+        g = np.stack([t.grad.cpu().numpy() for t in xs], axis=1)
+    assert tuple(S.shape) == (B,) + shape
+    np.testing.assert_array_equal(S.detach().cpu().numpy(), want)
+    np.testing.assert_array_equal(g, wantg)
+
+
+def test_shared_scheme_and_custom_weights(model):
+    """One scheme for the whole batch (the reference's literal per-batch scheme) and
+    caller-supplied group weights (group_fusion's second argument)."""
+    B, V, D, G = 6, 12, 512, 10
+    F, bins, dS = make_inputs(3, B, V, D, G, ties=True)
+    row = bins[0]
+    S = model.pool_fuse(dev(F), dev(row), G)
+    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, row, G))
+    rng = np.random.default_rng(9)
+    w = rng.uniform(0.5, 3.0, G).astype(np.float32)
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[row, np.arange(V)] = 1
+    views = [dev(F[:, v]) for v in range(V)]
+    S2 = model.group_fusion(model.view_pooling(views, dev(scheme)), dev(w))
+    want = O.group_fusion(O.view_pooling([F[:, v] for v in range(V)], scheme), w)
+    np.testing.assert_array_equal(S2.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("pool", ["max", "mean"])
+@pytest.mark.parametrize("B,V,D,G", [(17, 12, 2048, 8), (5, 20, 1024, 16), (3, 6, 72, 10), (2, 80, 1024, 8)])
+def test_bf16(model, pool, B, V, D, G):
+    F, bins, dS = make_inputs(B + V, B, V, D, G)
+    Fb, dSb = O.round_bf16(F), O.round_bf16(dS)
+    x = dev(Fb, torch.bfloat16).requires_grad_(True)
+    S = model.pool_fuse(x, dev(bins), G, pool=pool)
+    want = O.pool_fuse_fwd(Fb, bins, G, pool, 1.0)
+    got = S.detach().float().cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL_BF16, atol=RTOL_BF16 * np.abs(want).max())
+    np.testing.assert_array_equal(got, O.round_bf16(want))          # float32 math, one final rounding
+    S.backward(dev(dSb, torch.bfloat16))
+    wantg = O.pool_fuse_bwd(dSb, Fb, bins, G, pool)
+    np.testing.assert_array_equal(x.grad.float().cpu().numpy(), O.round_bf16(wantg))
+
+
+def test_basic_pool_identity(model):
+    """basic / simple pool (nets/model.py:202) = max over all views."""
+    F, _, _ = make_inputs(21, 4, 12, 256, 8)
+    S = model.basic_pool(dev(F))
+    np.testing.assert_array_equal(S.cpu().numpy(), F.max(axis=1))
+
+
+def test_tie_mask_matches_oracle(model):
+    from gvcnn_tf_b200.model import _Views, _pool_fuse_fwd
+    F, bins, _ = make_inputs(4, 5, 12, 1024, 8, ties=True)
+    fv = _Views(dev(F), "bvd", "F")
+    _, mask, _, _, _, _, _, _ = _pool_fuse_fwd(fv, dev(bins), 8, "max", 1.0, None, True, False)
+    np.testing.assert_array_equal(mask.cpu().numpy(), O.tie_mask_planes(F, bins, 8))
+
+
+# ---------------------------------------------------------------- score + bin
+def score_inputs(seed, B, V, Cr, bias_range=0.0):
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((B, V, Cr)).astype(np.float32)
+    lim = np.sqrt(6.0 / (Cr + 1))
+    W = rng.uniform(-lim, lim, (V, Cr)).astype(np.float32)
+    b = rng.uniform(-bias_range, bias_range, V).astype(np.float32) if bias_range else np.zeros(V, np.float32)
+    return R, W, b
+
+
+@pytest.mark.parametrize("B,V,Cr,G", [(512, 12, 1024, 8), (64, 6, 1024, 10), (32, 20, 1000, 16), (16, 80, 1024, 4),
+                                       (8, 12, 37, 2), (3, 5, 4100, 10)])
+def test_score_bin_shape_mode(model, c_oracle, B, V, Cr, G):
+    R, W, b = score_inputs(B + V + Cr, B, V, Cr, bias_range=0.5)
+    sr = model.score_bin(dev(R), dev(W), dev(b), G, edge_ulps=1)
+    x = sr.x.cpu().numpy()
+    # (1) the kernel's float32 summation order restated with fmaf: bit-exact x, scores and bins
+    E = 4 if Cr % 4 == 0 else 1
+    xk = c_oracle.view_score_x_kernel_order(R, W, b, E=E)
+    np.testing.assert_array_equal(x, xk)
+    sk = c_oracle.score_f32(xk)
+    np.testing.assert_array_equal(sr.scores.cpu().numpy(), sk)
+    np.testing.assert_array_equal(sr.bins.cpu().numpy(), O.bins_from_scores(sk, G))
+    # (2) against the float64 value of the mathematics: x within float32 dot-product error,
+    #     bins identical except where the float64 score sits on a bin edge (reported separately)
+    x64 = c_oracle.view_score_x_f64(R, W, b)
+    np.testing.assert_allclose(x, x64, rtol=0, atol=3e-5)
+    s64 = O.score_from_x(x64)
+    b64 = np.trunc(s64 * G).astype(np.int32)
+    mism = sr.bins.cpu().numpy() != b64
+    near = np.abs(s64 * G - np.round(s64 * G)) < 1e-4
+    assert (~mism | near).all()
+    print("score parity: %d views, %d bin mismatches vs float64 (all on edges), %d flagged within 1 ulp"
+          % (mism.size, int(mism.sum()), int(sr.near_edge().sum())))
+    np.testing.assert_array_equal(sr.near_edge().cpu().numpy(), O.edge_ulps_distance(sk, G, 1))
+
+
+def test_score_bf16_and_layouts(model, c_oracle):
+    B, V, Cr, G = 40, 12, 1024, 8
+    R, W, b = score_inputs(1, B, V, Cr)
+    Rb = O.round_bf16(R)
+    sr = model.score_bin(dev(Rb, torch.bfloat16), dev(W), dev(b), G)
+    np.testing.assert_array_equal(sr.x.cpu().numpy(), c_oracle.view_score_x_kernel_order(Rb, W, b, E=8))
+    sr2 = model.score_bin(dev(R.transpose(1, 0, 2)), dev(W), dev(b), G, layout="vbd")
+    sr3 = model.score_bin([dev(R[:, v]) for v in range(V)], dev(W), dev(b), G)
+    want = c_oracle.view_score_x_kernel_order(R, W, b, E=4)
+    np.testing.assert_array_equal(sr2.x.cpu().numpy(), want)
+    np.testing.assert_array_equal(sr3.x.cpu().numpy(), want)
+
+
+def test_score_edge_cases(model):
+    """|x| = 1 -> s = 0.5 exactly; x = 0 -> s = 0 -> bin 0; x = k/(G-k) flagged near-edge."""
+    G, V = 10, 12
+    W = np.zeros((V, 4), dtype=np.float32)
+    W[:, 0] = 1.0
+    xs = np.array([1.0, -1.0, 0.0, 1 / 9, 2 / 8, 3 / 7, 4 / 6, 5 / 5, 6 / 4, 7 / 3, 8 / 2, 9 / 1], dtype=np.float32)
+    R = np.zeros((1, V, 4), dtype=np.float32)
+    R[0, :, 0] = xs
+    sr = model.score_bin(dev(R), dev(W), dev(np.zeros(V, np.float32)), G, edge_ulps=1)
+    s = sr.scores.cpu().numpy()[0]
+    assert s[0] == 0.5 and s[1] == 0.5 and s[2] == 0.0
+    bins = sr.bins.cpu().numpy()[0]
+    assert bins[0] == 5 and bins[2] == 0
+    want_s = O.score_from_x_rational(xs)
+    np.testing.assert_array_equal(s, want_s)
+    np.testing.assert_array_equal(bins, O.bins_from_scores(want_s, G))
+    assert sr.near_edge().cpu().numpy()[0][3:].all()
+
+
+def test_score_batch_mode(model, c_oracle):
+    """Literal nets/model.py:146: one score per view from the batch mean."""
+    B, V, Cr, G = 300, 12, 1024, 10
+    R, W, b = score_inputs(8, B, V, Cr, bias_range=4.0)
+    sr = model.score_bin(dev(R), dev(W), dev(b), G, score_reduce="batch")
+    x64 = c_oracle.view_score_x_f64(R, W, b).mean(axis=0)
+    np.testing.assert_allclose(sr.x.cpu().numpy()[0], x64, rtol=0, atol=2e-5)
+    s64 = O.score_from_x(x64)
+    b64 = np.trunc(s64 * G).astype(np.int32)
+    got = sr.bins.cpu().numpy()[0]
+    near = np.abs(s64 * G - np.round(s64 * G)) < 1e-4
+    assert ((got == b64) | near).all()
+    assert tuple(sr.bins.shape) == (1, V)
+    # the reference-shaped flow: scores -> group_scheme -> group_weight -> pooling -> fusion
+    scores = model.view_scores(dev(R), dev(W), dev(b))
+    np.testing.assert_array_equal(scores.cpu().numpy(), sr.scores.cpu().numpy())
+    scheme = model.group_scheme([scores[0]], G, V)
+    F, _, _ = make_inputs(2, B, V, 256, G)
+    S = model.group_fusion(model.view_pooling([dev(F[:, v]) for v in range(V)], scheme), model.group_weight(scheme))
+    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, got, G))
+
+
+# ---------------------------------------------------------------- whole path, full size
+def test_full_path_config2_properties(model, c_oracle):
+    """BASELINE configs[1] size (B=4096, V=12, D=2048, G=8): C oracle on the full batch plus
+    size-independent properties."""
+    B, V, D, G, Cr = 4096, 12, 2048, 8, 1024
+    g = torch.Generator().manual_seed(0)
+    F = torch.randn((B, V, D), generator=g)
+    R = torch.randn((B, V, Cr), generator=torch.Generator().manual_seed(1))
+    lim = float(np.sqrt(6.0 / (Cr + 1)))
+    W = (torch.rand((V, Cr), generator=torch.Generator().manual_seed(2)) * 2 - 1) * lim
+    b = torch.zeros(V)
+    Fd = F.cuda().requires_grad_(True)
+    S, sr = model.grouping_fusion(R.cuda(), W.cuda(), b.cuda(), Fd, G)
+    bins = sr.bins.cpu().numpy()
+    assert bins.min() >= 0 and bins.max() < G and len(np.unique(bins)) >= G - 1
+    xk = c_oracle.view_score_x_kernel_order(R.numpy(), W.numpy(), b.numpy(), E=4)
+    np.testing.assert_array_equal(bins, O.bins_from_scores(c_oracle.score_f32(xk), G))
+    want = c_oracle.pool_fuse_fwd(F.numpy(), bins, G, "max", 1.0)
+    np.testing.assert_array_equal(S.detach().cpu().numpy(), want)
+    dS = torch.randn((B, D), generator=torch.Generator().manual_seed(3))
+    S.backward(dS.cuda())
+    dF = Fd.grad
+    np.testing.assert_array_equal(dF.cpu().numpy(), c_oracle.pool_fuse_bwd(dS.numpy(), F.numpy(), bins, G, "max"))
+    # property: the gradient mass of each group is w_g/(G+V) * dS (ties share, nothing is lost)
+    onehot = torch.nn.functional.one_hot(sr.bins.long(), G).float()           # [B, V, G]
+    cnt = onehot.sum(dim=1)                                                  # [B, G]
+    mass = torch.einsum("bvd,bvg->bgd", dF, onehot)
+    want_mass = ((1 + cnt) * (cnt > 0) / (G + V))[:, :, None] * dS.cuda()[:, None, :]
+    torch.testing.assert_close(mass, want_mass, rtol=1e-5, atol=1e-6)
+    # property: shape independence - any sub-batch gives the same rows
+    idx = torch.tensor([0, 17, 4095, 2048])
+    S_sub = model.pool_fuse(F[idx].cuda(), sr.bins[idx.cuda()], G)
+    assert torch.equal(S_sub, S.detach()[idx.cuda()])
+    # property: mean mode is linear in F
+    Sm1 = model.pool_fuse(F.cuda(), sr.bins, G, pool="mean", empty_fill=0.0)
+    Sm2 = model.pool_fuse((2 * F).cuda(), sr.bins, G, pool="mean", empty_fill=0.0)
+    assert torch.equal(Sm2, 2 * Sm1)
+
+
+def test_host_buffer_entry_point(model):
+    """gvcnn_grouping_fusion_host: pinned host buffers in, host buffers out, same bits as the
+    device-pointer path."""
+    import ctypes
+    from gvcnn_tf_b200 import _cabi as Cb
+    B, V, D, G, Cr = 600, 12, 512, 8, 256
+    F, _, dS = make_inputs(31, B, V, D, G, ties=True)
+    R, W, b = score_inputs(32, B, V, Cr)
+    Fh, Rh, dSh = (torch.tensor(a).pin_memory() for a in (F, R, dS))
+    Sh = torch.empty((B, D)).pin_memory()
+    dFh = torch.empty((B, V, D)).pin_memory()
+    sc = torch.empty((B, V)).pin_memory()
+    bn = torch.empty((B, V), dtype=torch.int32).pin_memory()
+    st = torch.zeros(4, dtype=torch.int32)
+    Wd, bd = dev(W), dev(b)
+    L = Cb.lib()
+    chunk = 256
+    nbytes = L.gvcnn_host_workspace_bytes(chunk, V, Cr, D, Cb.F32, 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = L.gvcnn_grouping_fusion_host(p(Rh), p(Fh), p(Wd), p(bd), p(Sh), p(sc), p(bn), p(dSh), p(dFh), p(st),
+                                      B, V, Cr, D, G, Cb.POOL_MAX, ctypes.c_float(1.0), Cb.F32, chunk, p(ws), nbytes)
+    assert rc == 0, L.gvcnn_strerror(rc)
+    sr = model.score_bin(dev(R), Wd, bd, G)
+    np.testing.assert_array_equal(bn.numpy(), sr.bins.cpu().numpy())
+    np.testing.assert_array_equal(Sh.numpy(), O.pool_fuse_fwd(F, bn.numpy(), G))
+    np.testing.assert_array_equal(dFh.numpy(), O.pool_fuse_bwd(dS, F, bn.numpy(), G))
+
+
+def test_head_module_trains(model):
+    """GVCNNHead: scores, shape descriptor, logits like nets/model.py:166; backward reaches the view
+    descriptors and the classifier, not the score FC."""
+    torch.manual_seed(0)
+    N, V, Cr, Cf, G = 6, 12, 64, 32, 10
+    head = model.GVCNNHead(V, Cr, Cf, 5, num_group=G).cuda()
+    with torch.no_grad():
+        head.score_bias.uniform_(-3, 3)
+    raw = torch.randn(N, V, Cr, device="cuda")
+    final = [torch.randn(N, 3, 3, Cf, device="cuda", requires_grad=True) for _ in range(V)]
+    scores, S, logits = head(raw, final)
+    assert tuple(scores.shape) == (1, V) and tuple(S.shape) == (N, 3, 3, Cf) and tuple(logits.shape) == (N, 5)
+    torch.nn.functional.cross_entropy(logits, torch.arange(N, device="cuda") % 5).backward()
+    assert all(f.grad is not None and torch.isfinite(f.grad).all() for f in final)
+    assert head.classifier.weight.grad is not None and head.score_kernel.grad is None
+    # same numbers through the reference-shaped call sequence
+    scheme = model.group_scheme([scores[0]], G, V)
+    s2, S2, logits2 = model.gvcnn_head(raw, final, head, group_scheme=scheme, group_weight=model.group_weight(scheme))
+    assert torch.equal(S2, S) and torch.equal(logits2, logits)
