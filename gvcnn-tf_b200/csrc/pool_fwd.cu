@@ -208,7 +208,7 @@ static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
 #define GVCNN_LAUNCH_FWD(VEC_, POOL_, MASK_, BULK_)                                                        \
     do {                                                                                                   \
         auto kern = pool_fuse_fwd_kernel<T, VEC_, POOL_, MASK_, BULK_>;                                    \
-        if (smem > 48 * 1024)                                                                              \
+        if (smem + 8192 > 48 * 1024)                                                                            \
             err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (err == cudaSuccess)                                                                            \
             kern<<<(unsigned)(B * tiles), nt, smem, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),      \
