@@ -46,6 +46,36 @@ __device__ __forceinline__ void build_plan(Plan &pl, const int32_t *__restrict__
         }
         pl.sumw = sw;
     }
+    if (V <= 32) {
+        // warp 0 ranks the views with shuffles: no shared-memory round trip, one barrier
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            int b = 0x7fffffff;
+            if (lane < V) {
+                b = __ldg(bins + lane);
+                if (b < 0 || b >= G) {
+                    if (status) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+                    b = b < 0 ? 0 : G - 1;
+                }
+            }
+            int below = 0, same_before = 0, same = 0;
+            for (int u = 0; u < V; ++u) {
+                const int bu = __shfl_sync(0xffffffffu, b, u);
+                below += (bu < b);
+                same += (bu == b);
+                same_before += (bu == b) & (u < lane);
+            }
+            if (lane < V) {
+                const int k = below + same_before;
+                pl.order[k] = (uint8_t)lane;
+                pl.gbin[k] = b;
+                pl.glen[k] = (uint16_t)same;
+                pl.gw[k] = weights ? __ldg(weights + b) : (float)(1 + same);
+            }
+        }
+        __syncthreads();
+        return;
+    }
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
         int b = __ldg(bins + v);
         if (b < 0 || b >= G) {

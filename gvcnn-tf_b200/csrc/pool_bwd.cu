@@ -26,24 +26,34 @@ template <> struct PlaneWord<8> { using type = uint2; };
 template <> struct PlaneWord<4> { using type = uint32_t; };
 template <> struct PlaneWord<1> { using type = uint8_t; };
 
-template <int E>
-__device__ __forceinline__ uint32_t tie_bit(const typename PlaneWord<E>::type &w, int e, int bit)
+// A plane word carries, for each of 4 (or 8) consecutive descriptor elements, one byte whose bit i
+// is the tie bit of sorted view position 8*plane + i.  The helpers below work on all 4 bytes of a
+// 32-bit word at once.
+__device__ __forceinline__ uint32_t word_of(const uint2 &w, int i) { return i ? w.y : w.x; }
+__device__ __forceinline__ uint32_t word_of(const uint32_t &w, int) { return w; }
+__device__ __forceinline__ uint32_t word_of(const uint8_t &w, int) { return (uint32_t)w; }
+
+// 0xFFFFFFFF if byte e of `msb4` has its top bit set, else 0 (PRMT sign replication)
+__device__ __forceinline__ uint32_t byte_msb_to_mask(uint32_t msb4, int e)
 {
-    if constexpr (E == 8) return (((e < 4) ? w.x : w.y) >> (8 * (e & 3) + bit)) & 1u;
-    else if constexpr (E == 4) return (w >> (8 * e + bit)) & 1u;
-    else return ((uint32_t)w >> bit) & 1u;
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(msb4), "r"(0u), "r"(0x8888u + 0x1111u * (uint32_t)e));
+    return r;
 }
 
 template <typename T, bool VEC, int POOL>
 __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins,
                                      const int64_t bin_sb, const uint8_t *__restrict__ mask,
-                                     const float *__restrict__ weights, const int64_t w_sb, const ViewPtrs gp, const int64_t g_sb, int32_t *status, const int B,
-                                     const int V, const int64_t D, const int G, const int tiles_per_shape)
+                                     const float *__restrict__ weights, const int64_t w_sb, const ViewPtrs gp,
+                                     const int64_t g_sb, int32_t *status, const int B, const int V,
+                                     const int64_t D, const int G, const int tiles_per_shape)
 {
     constexpr int E = VEC ? Elem<T>::kVec : 1;
+    constexpr int NW = (E + 3) / 4;  // 32-bit words per plane word
     using PW = typename PlaneWord<E>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Plan plan;
+    __shared__ float rcp_tab[GVCNN_MAX_VIEWS + 1];  // rcp_tab[n] = 1 / n, IEEE division
 
     const int NT = blockDim.x;
     const int TD = NT * E;
@@ -54,7 +64,7 @@ __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__
     const int e0 = threadIdx.x * E;
     const bool active = e0 < n_valid;
     const int64_t off = (int64_t)b * D + d0 + e0;
-    PW *slot = reinterpret_cast<PW *>(smem_raw);  // [P][NT]
+    PW *slot = reinterpret_cast<PW *>(smem_raw);  // [P][NT], thread-private columns
     const int P = (V + 7) >> 3;
 
     float t[E];
@@ -69,12 +79,16 @@ __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__
                 slot[p * NT + threadIdx.x] = *reinterpret_cast<const PW *>(mask + ((int64_t)p * B) * D + off);
         }
     }
+    if constexpr (POOL == GVCNN_POOL_MAX) {
+        for (int n = threadIdx.x; n <= V; n += NT) rcp_tab[n] = __fdiv_rn(1.0f, (float)n);
+    }
     build_plan(plan, bins + (int64_t)b * bin_sb, V, G, status, weights ? weights + (int64_t)b * w_sb : nullptr);
     if (!active) return;
 
     const float sumw = plan.sumw;
 #pragma unroll
     for (int e = 0; e < E; ++e) t[e] = __fdiv_rn(t[e], sumw);
+    const int64_t row_off = ((int64_t)b * g_sb + d0 + e0) * (int64_t)sizeof(T);
 
     int k = 0;
     while (k < V) {
@@ -84,26 +98,36 @@ __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__
 #pragma unroll
         for (int e = 0; e < E; ++e) val[e] = __fmul_rn(t[e], w);
         if constexpr (POOL == GVCNN_POOL_MAX) {
-            int nsel[E];
+            // pass 1: how many views of the group attain the max, per element (byte-parallel counters)
+            uint32_t cnt[NW];
 #pragma unroll
-            for (int e = 0; e < E; ++e) nsel[e] = 0;
+            for (int i = 0; i < NW; ++i) cnt[i] = 0u;
             for (int j = 0; j < len; ++j) {
                 const int kk = k + j;
                 const PW wd = slot[(kk >> 3) * NT + threadIdx.x];
 #pragma unroll
-                for (int e = 0; e < E; ++e) nsel[e] += (int)tie_bit<E>(wd, e, kk & 7);
+                for (int i = 0; i < NW; ++i) cnt[i] += (word_of(wd, i) >> (kk & 7)) & 0x01010101u;
             }
 #pragma unroll
-            for (int e = 0; e < E; ++e) val[e] = __fmul_rn(__fdiv_rn(1.0f, (float)nsel[e]), val[e]);
+            for (int e = 0; e < E; ++e) {
+                const uint32_t nsel = (cnt[e >> 2] >> (8 * (e & 3))) & 0xffu;
+                val[e] = __fmul_rn(rcp_tab[nsel], val[e]);  // (1 / num_selected) * g1; 1 * g1 == g1
+            }
+            // pass 2: route
             for (int j = 0; j < len; ++j) {
                 const int kk = k + j;
                 const PW wd = slot[(kk >> 3) * NT + threadIdx.x];
                 float o[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) o[e] = tie_bit<E>(wd, e, kk & 7) ? val[e] : 0.0f;
-                T *dst = reinterpret_cast<T *>(gp.p[plan.order[kk]]) + (int64_t)b * g_sb + d0 + e0;
+                for (int i = 0; i < NW; ++i) {
+                    const uint32_t msb4 = (word_of(wd, i) << (7 - (kk & 7))) & 0x80808080u;
+#pragma unroll
+                    for (int e = 4 * i; e < 4 * i + 4 && e < E; ++e)
+                        o[e] = __uint_as_float(__float_as_uint(val[e]) & byte_msb_to_mask(msb4, e & 3));
+                }
+                char *dst = gp.p[plan.order[kk]] + row_off;
                 if constexpr (VEC) stg_stream_16(dst, Elem<T>::pack(o));
-                else *dst = Elem<T>::from_float(o[0]);
+                else *reinterpret_cast<T *>(dst) = Elem<T>::from_float(o[0]);
             }
         } else {
 #pragma unroll
@@ -111,9 +135,9 @@ __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__
             uint4 packed;
             if constexpr (VEC) packed = Elem<T>::pack(val);
             for (int j = 0; j < len; ++j) {
-                T *dst = reinterpret_cast<T *>(gp.p[plan.order[k + j]]) + (int64_t)b * g_sb + d0 + e0;
+                char *dst = gp.p[plan.order[k + j]] + row_off;
                 if constexpr (VEC) stg_stream_16(dst, packed);
-                else *dst = Elem<T>::from_float(val[0]);
+                else *reinterpret_cast<T *>(dst) = Elem<T>::from_float(val[0]);
             }
         }
         k += len;

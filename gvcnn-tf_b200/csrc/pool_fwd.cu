@@ -137,13 +137,20 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
             else *pp = Elem<T>::from_float(m[0]);
         }
         if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+            // second pass over the group's columns (shared memory, not HBM): 4 elements' tie
+            // bits are assembled byte-parallel in one word and shifted to the view's bit
             for (int j = 0; j < len; ++j) {
                 const int kk = k + j;
                 float x[E];
                 load_col<T, VEC>(stage, plan.order[kk], TD, e0, x);
 #pragma unroll
-                for (int e = 0; e < E; ++e)
-                    pw[e >> 2] |= (uint32_t)(x[e] == m[e]) << (8 * (e & 3) + (kk & 7));
+                for (int i = 0; i < (E + 3) / 4; ++i) {
+                    uint32_t sel4 = 0u;
+#pragma unroll
+                    for (int e = 4 * i; e < 4 * i + 4 && e < E; ++e)
+                        sel4 |= (x[e] == m[e]) ? (1u << (8 * (e & 3))) : 0u;
+                    pw[i] |= sel4 << (kk & 7);
+                }
                 if ((kk & 7) == 7 || kk == V - 1) {
                     uint8_t *mp = mask + ((int64_t)(kk >> 3) * B) * D + out_off;
                     if constexpr (E == 8) {
