@@ -105,7 +105,7 @@ int gvcnn_check_device(void)
 
 int gvcnn_set_pool_variant(int variant)
 {
-    if (variant < 0 || variant > 2) return GVCNN_E_BAD_MODE;
+    if (variant < 0 || variant > 3) return GVCNN_E_BAD_MODE;
     g_pool_variant.store(variant);
     return 0;
 }
@@ -207,6 +207,13 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     al = al && is_aligned(S, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8)) &&
          (!group_desc || is_aligned(group_desc, 16));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
+    const int variant = g_pool_variant.load();
+    if (al && !weights && !group_desc && (variant == 0 || variant == 3)) {
+        // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu)
+        rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool,
+                                       empty_fill, dtype, static_cast<cudaStream_t>(stream));
+        if (rc != -1000) return rc;
+    }
     return launch_pool_fuse_fwd(fp, sb, bins, bin_stride_b, S, group_desc, tie_mask, weights, weight_stride_b, status, B, V, D, G, pool, empty_fill,
                                 dtype, al, g_pool_variant.load(), static_cast<cudaStream_t>(stream));
 }

@@ -166,6 +166,26 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         : "memory");
 }
 
+// ---- exact division with a precomputed reciprocal -----------------------------
+// a / b, correctly rounded (== __fdiv_rn(a, b)), given rcp_b = __frcp_rn(b) =
+// RN(1/b): q = RN(a * rcp_b) is within 1 ulp of a / b, the remainder r = a - b*q
+// is exact in one FMA, and RN(q + r * rcp_b) is the correctly rounded quotient
+// (Markstein).  That argument needs a, q and r to stay clear of overflow and of
+// the subnormal range, so operands outside 2^-100 <= |a| < 2^100 (and 0, inf,
+// NaN) take the IEEE division instruction sequence instead.  b is a small positive
+// integer here (G + V, a group size, or a tie count).  tests/test_gpu_div.py
+// checks this against __fdiv_rn for every float a and every b in use.
+__device__ __forceinline__ float div_by_rcp(float a, float b, float rcp_b)
+{
+    const uint32_t ea = (__float_as_uint(a) >> 23) & 0xffu;  // biased exponent
+    if (ea - 27u < 200u) {                                   // 2^-100 <= |a| < 2^100
+        const float q = __fmul_rn(a, rcp_b);
+        const float r = __fmaf_rn(-b, q, a);
+        return __fmaf_rn(r, rcp_b, q);
+    }
+    return __fdiv_rn(a, b);
+}
+
 // ---- element packing ---------------------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {
@@ -225,6 +245,9 @@ int launch_group_weight(const int32_t *bins, float *weights, int rows, int V, in
 int launch_pool_fuse_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
                          void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool,
                          float fill, int dtype, bool aligned16, int variant, cudaStream_t st);
+int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                              uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
+                              float fill, int dtype, cudaStream_t st);
 int launch_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
                          const float *weights, int64_t w_sb,
                          const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,

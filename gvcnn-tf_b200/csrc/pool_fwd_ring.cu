@@ -1,0 +1,336 @@
+// Pooling + fusion forward, fast path: persistent, warp-specialised, TMA-fed ring.
+//
+// Same arithmetic and op order as pool_fwd.cu (nets/model.py:28-102; see there),
+// different plumbing.  One CTA per SM stays resident and walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = TD consecutive descriptor
+// elements of one shape, all V views).  Roles:
+//   * producer warp: prefetches the shape's V bins, ranks the views by
+//     (bin, view) with warp shuffles, waits for a free ring slot, publishes the
+//     per-tile plan, and then lanes 0..V-1 each fire ONE 1-D bulk async copy
+//     (cp.async.bulk, the TMA engine) that lands "their" view's row in the slot
+//     at its SORTED position - so consumers read rows k = 0..V-1 in bin order
+//     at fixed offsets, with no index indirection;
+//   * 8 consumer warps: wait on the slot's full barrier, reduce their 16-byte
+//     column group by group in float32 registers, release the slot, then do
+//     the division and the streaming store.
+// The ring (4 slots x 48 KB at V = 12, fp32) keeps ~150-190 KB of loads in
+// flight per SM continuously; there is no per-tile prologue bubble and no
+// wave tail.  Used when rows are 16-byte aligned, V <= 32, the reference's own
+// group weights are wanted and no per-group descriptors are requested; every
+// other case takes the generic kernel in pool_fwd.cu.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace gvcnn {
+
+constexpr int kRingProducerThreads = 32;
+
+// Per-slot plan written by the producer warp, read by the consumers.
+struct __align__(16) RingPlan {
+    uint32_t first_mask;  // bit k: the k-th sorted view starts a group
+    uint32_t tail_skip;   // empty groups after the last non-empty one
+    uint32_t pad[2];
+    uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// V and the consumer count are compile-time: rows sit at immediate offsets, every loop over views is
+// fully unrolled, and the only data-dependent control flow left is one uniform branch per view
+// ("does this view start a group?").  MINB = CTAs per SM the register budget is sized for.
+template <typename T, int POOL, bool MASK, int V, int NCONS, int MINB>
+__global__ void __launch_bounds__(NCONS + kRingProducerThreads, MINB)
+pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
+                          const int64_t bin_sb, T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
+                          const int B, const int64_t D, const int G, const float fill,
+                          const int tiles_per_shape, const int num_tiles, const int stages)
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr int NW = (E + 3) / 4;
+    constexpr int P = (V + 7) / 8;
+    constexpr int kMaxStages = 8;
+    constexpr int TD = NCONS * E;
+    constexpr uint32_t kRowStride = (uint32_t)NCONS * 16u;   // bytes between sorted rows in a slot
+    constexpr uint32_t kStageBytes = kRowStride * (uint32_t)V;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ RingPlan plans[kMaxStages];
+    __shared__ int32_t sorted_bin[32];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], (uint32_t)(NCONS >> 5));
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tile walk shared by both roles: t = blockIdx.x + it * gridDim.x, kept as (shape b, tile in shape)
+    const int step_b = (int)gridDim.x / tiles_per_shape;
+    const int step_t = (int)gridDim.x - step_b * tiles_per_shape;
+    int b = (int)blockIdx.x / tiles_per_shape;
+    int tile = (int)blockIdx.x - b * tiles_per_shape;
+    int s = 0;
+    uint32_t ph = 0;
+
+    if ((int)threadIdx.x >= NCONS) {
+        // ------------------------------------------------------------------ producer warp
+        const int lane = threadIdx.x & 31;
+        int nb = 0x7fffffff;
+        if ((int)blockIdx.x < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b * bin_sb + lane);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int64_t d0 = (int64_t)tile * TD;
+            const uint32_t row_bytes = (uint32_t)min((int64_t)TD, D - d0) * sizeof(T);
+            int bin = nb;
+            // next tile's coordinates; prefetch its bins behind this tile's work
+            int b_n = b + step_b, tile_n = tile + step_t;
+            if (tile_n >= tiles_per_shape) { tile_n -= tiles_per_shape; ++b_n; }
+            if (t + (int)gridDim.x < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b_n * bin_sb + lane);
+            if (lane < V && (bin < 0 || bin >= G)) {
+                if (status && tile == 0) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+                bin = bin < 0 ? 0 : G - 1;
+            }
+            int below = 0, same_before = 0;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const int bu = __shfl_sync(0xffffffffu, bin, u);
+                below += (bu < bin);
+                same_before += (bu == bin) & (u < lane);
+            }
+            const int k = below + same_before;
+            const bool first = lane < V && same_before == 0;
+            const uint32_t fm = __reduce_or_sync(0xffffffffu, first ? (1u << k) : 0u);
+            if (lane < V) sorted_bin[k] = bin;
+            __syncwarp();
+            const int prev = (lane < V && k > 0) ? sorted_bin[k - 1] : -1;
+            const int last_bin = sorted_bin[V - 1];
+            if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1u);  // slot drained by all consumer warps
+            __syncwarp();
+            if (lane < V) plans[s].skip[k] = (uint8_t)(first ? bin - prev - 1 : 0);
+            if (lane == 0) {
+                plans[s].first_mask = fm;
+                plans[s].tail_skip = (uint32_t)(G - 1 - last_bin);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full_bar[s], row_bytes * (uint32_t)V);
+            __syncwarp();
+            if (lane < V)
+                bulk_g2s(smem_raw + (size_t)s * kStageBytes + (size_t)k * kRowStride,
+                         fp.p[lane] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &full_bar[s]);
+            b = b_n;
+            tile = tile_n;
+            if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int e0 = threadIdx.x * E;
+    const float sumw = (float)(G + V);  // sum_g (1 + n_g): exact in float32 in any order
+    const float rcp_sumw = __frcp_rn(sumw);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int64_t d0 = (int64_t)tile * TD;
+        const bool active = (int64_t)e0 < D - d0;
+        const int64_t out_off = (int64_t)b * D + d0 + e0;
+        const unsigned char *col = smem_raw + (size_t)s * kStageBytes + (size_t)threadIdx.x * 16;
+
+        mbar_wait(&full_bar[s], ph);
+
+        float acc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+        if (active) {
+            const uint32_t fm = plans[s].first_mask;
+            const uint32_t tail_skip = plans[s].tail_skip;
+            uint32_t skw[(V + 3) / 4];
+#pragma unroll
+            for (int i = 0; i < (V + 3) / 4; ++i) skw[i] = reinterpret_cast<const uint32_t *>(plans[s].skip)[i];
+            // all V rows of this thread's column, in bin order, fetched in one batch
+            uint4 raw[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
+
+            float m[E];
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float x[E];
+                Elem<T>::unpack(raw[k], x);
+                if (k == 0 || ((fm >> k) & 1u)) {  // uniform: this view starts a group
+                    if (k > 0) {                   // close the previous group: acc += w_g * P_g
+                        const float w = (float)(1 + cnt);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
+                            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                        }
+                    }
+                    if (fill != 0.0f) {  // empty groups in between: w = 1, P = fill
+                        const int nskip = (int)((skw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                        for (int q = 0; q < nskip; ++q) {
+#pragma unroll
+                            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; ++e) m[e] = x[e];
+                    cnt = 1;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+                    ++cnt;
+                }
+                // keep the running (prefix) max of the group where the row was: at a group's last
+                // member it is the group max, which the tie sweep below needs (exact in T)
+                if constexpr (MASK && POOL == GVCNN_POOL_MAX) raw[k] = Elem<T>::pack(m);
+            }
+            {
+                const float w = (float)(1 + cnt);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
+                    acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                }
+                if (fill != 0.0f)
+                    for (uint32_t q = 0; q < tail_skip; ++q) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                    }
+            }
+            if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+                // tie sweep, last view to first: gm = max of the group the view is in; bit k of the
+                // mask <=> view k attains it.  Rows are re-read from the slot (shared memory).
+                uint32_t pw[P][NW];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) pw[p][i] = 0u;
+                float gm[E];
+#pragma unroll
+                for (int k = V - 1; k >= 0; --k) {
+                    const bool last = (k == V - 1) || ((fm >> (k + 1)) & 1u);
+                    if (last) Elem<T>::unpack(raw[k], gm);
+                    float x[E];
+                    Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + k * kRowStride), x);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (x[e] == gm[e]) pw[k >> 3][e >> 2] |= 1u << (8 * (e & 3) + (k & 7));
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    uint8_t *mp = mask + ((int64_t)p * B) * D + out_off;
+                    if constexpr (E == 8) *reinterpret_cast<uint2 *>(mp) = make_uint2(pw[p][0], pw[p][1]);
+                    else *reinterpret_cast<uint32_t *>(mp) = pw[p][0];
+                }
+            }
+        }
+        // every lane of the warp is done reading the slot: hand it back to the producer
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = div_by_rcp(acc[e], sumw, rcp_sumw);
+            stg_stream_16(S + out_off, Elem<T>::pack(acc));
+        }
+        b += step_b;
+        tile += step_t;
+        if (tile >= tiles_per_shape) { tile -= tiles_per_shape; ++b; }
+        if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+}
+
+static int ring_sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            return 148;
+        }
+        cached = n;
+    }
+    return cached;
+}
+
+template <typename T, int V, int NCONS, int MINB>
+static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                         uint8_t *mask, int32_t *status, int B, int64_t D, int G, int pool, float fill,
+                         cudaStream_t st)
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr size_t stage_bytes = (size_t)V * NCONS * 16;
+    // shared memory an SM can give to MINB co-resident CTAs of this kernel (1 KB reserved + ~1.3 KB static each)
+    int stages = (int)(((226 * 1024) / MINB - 3 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (const char *env = getenv("GVCNN_RING_STAGES")) {  // tuning knob for A/B runs
+        const int want = atoi(env);
+        if (want >= 2 && want <= stages) stages = want;
+    }
+    if (stages < 2) return -1000;
+    const int64_t td = (int64_t)NCONS * E;
+    const int64_t tps = (D + td - 1) / td;
+    const int64_t tiles = (int64_t)B * tps;
+    if (tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
+    const size_t smem = stage_bytes * stages;
+    const int64_t max_grid = (int64_t)ring_sm_count() * MINB;
+    const int grid = (int)(tiles < max_grid ? tiles : max_grid);
+    const bool want_mask = (mask != nullptr) && pool == GVCNN_POOL_MAX;
+    cudaError_t err = cudaSuccess;
+#define GVCNN_LAUNCH_RING(POOL_, MASK_)                                                                      \
+    do {                                                                                                     \
+        auto kern = pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, V, NCONS, MINB>;                              \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (err == cudaSuccess)                                                                              \
+            kern<<<grid, NCONS + kRingProducerThreads, smem, st>>>(fp, f_sb, bins, bin_sb,                   \
+                                                                  static_cast<T *>(S), mask, status, B, D,  \
+                                                                  G, fill, (int)tps, (int)tiles, stages);   \
+    } while (0)
+    if (pool == GVCNN_POOL_MAX) {
+        if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false);
+    } else {
+        GVCNN_LAUNCH_RING(GVCNN_POOL_MEAN, false);
+    }
+#undef GVCNN_LAUNCH_RING
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                         uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
+                         cudaStream_t st)
+{
+    // the view counts of the reference's configurations (train.py:96 default 6; BASELINE sweep 6/12/20)
+    if (D < 256 * Elem<T>::kVec) return -1000;  // tiles narrower than one consumer row: generic kernel
+    switch (V) {
+    case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 12: return launch_ring_v<T, 12, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 20: return launch_ring_v<T, 20, 256, 1>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    default: return -1000;
+    }
+}
+
+// returns -1000 when this fast path does not apply
+int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
+                              uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
+                              float fill, int dtype, cudaStream_t st)
+{
+    if (V > 32 || G > 255) return -1000;
+    if (dtype == GVCNN_F32) {
+        if (D % 4) return -1000;
+        return launch_ring_t<float>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, st);
+    }
+    if (D % 8) return -1000;
+    return launch_ring_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, st);
+}
+
+}  // namespace gvcnn

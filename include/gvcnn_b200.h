@@ -178,9 +178,11 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
                         int B, int V, int64_t D, int G, int pool,
                         int g_layout, int dtype, void *stream);
 
-/* Which pooling kernel variant the next calls use: 0 = auto, 1 = bulk-copy
- * (TMA, cp.async.bulk) staged, 2 = plain vector loads staged through shared
- * memory.  Process-wide, for A/B measurement only. */
+/* Which forward pooling kernel the next calls use: 0 = auto (3 when it applies,
+ * else 1, else 2), 1 = one tile per CTA, bulk-copy (TMA, cp.async.bulk) staged,
+ * 2 = one tile per CTA, plain vector loads staged through shared memory,
+ * 3 = persistent warp-specialised TMA ring.  Process-wide, for A/B measurement
+ * and tests only. */
 int gvcnn_set_pool_variant(int variant);
 
 /* --- host-buffer path (end-to-end) ---------------------------------------

@@ -71,7 +71,7 @@ def test_argument_errors_before_any_launch(cabi):
     odd = ctypes.c_void_p(p.value + 2)
     assert L.gvcnn_pool_fuse_fwd(odd, p, 12, None, 0, p, None, None, None, 4, 12, 64, 8, 0, 1.0, 0, 0, None) == -6
     assert L.gvcnn_score_bin_fwd(p, None, p, None, p, p, None, None, 4, 12, 64, 8, 0, 0, 1, 0, None) == -1
-    assert L.gvcnn_set_pool_variant(5) == -8 and L.gvcnn_set_pool_variant(0) == 0
+    assert L.gvcnn_set_pool_variant(7) == -8 and L.gvcnn_set_pool_variant(0) == 0
     assert L.gvcnn_host_workspace_bytes(256, 12, 1024, 2048, 0, 0) > 256 * 12 * 2048 * 4 * 3
     assert L.gvcnn_host_workspace_bytes(0, 12, 1024, 2048, 0, 0) == 0
     if not torch.cuda.is_available():

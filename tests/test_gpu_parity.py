@@ -129,18 +129,24 @@ def test_pool_fuse_fwd_bwd_bit_exact_f32(model, pool, fill, B, V, D, G):
     np.testing.assert_array_equal(Ft.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("pool", ["max", "mean"])
-def test_pool_variants_agree(model, variant, pool):
-    """bulk-copy (TMA) staging and plain-load staging are the same function."""
+@pytest.mark.parametrize("B,V,D,G", [(19, 12, 2048, 8), (700, 12, 2048, 8), (301, 6, 1028, 10), (150, 20, 1024, 16),
+                                       (40, 32, 520, 4)])
+def test_pool_variants_agree(model, variant, pool, B, V, D, G):
+    """One-tile-per-CTA bulk-copy staging, plain-load staging and the persistent TMA ring are the
+    same function (forward, tie mask and therefore backward)."""
     from gvcnn_tf_b200 import _cabi
-    F, bins, dS = make_inputs(77, 19, 12, 2048, 8, ties=True)
+    F, bins, dS = make_inputs(77 + B, B, V, D, G, ties=True)
+    x = dev(F).requires_grad_(True)
     try:
         assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
-        S = model.pool_fuse(dev(F), dev(bins), 8, pool=pool)
+        S = model.pool_fuse(x, dev(bins), G, pool=pool)
     finally:
         _cabi.lib().gvcnn_set_pool_variant(0)
-    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, bins, 8, pool, 1.0))
+    np.testing.assert_array_equal(S.detach().cpu().numpy(), O.pool_fuse_fwd(F, bins, G, pool, 1.0))
+    S.backward(dev(dS))
+    np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
 
 
 @pytest.mark.parametrize("layout", ["bvd", "vbd", "list"])
