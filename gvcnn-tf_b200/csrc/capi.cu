@@ -236,6 +236,13 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     if (rc) return rc;
     al = al && is_aligned(dS, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
+    const int variant = g_pool_variant.load();
+    if (al && !weights && (variant == 0 || variant == 3)) {
+        // fast path: V-templated kernel (pool_bwd_fast.cu)
+        rc = launch_pool_fuse_bwd_fast(dS, bins, bin_stride_b, tie_mask, gp, sb, status, B, V, D, G, pool, dtype,
+                                       static_cast<cudaStream_t>(stream));
+        if (rc != -1000) return rc;
+    }
     return launch_pool_fuse_bwd(dS, bins, bin_stride_b, tie_mask, weights, weight_stride_b, gp, sb, status, B, V, D, G, pool, dtype, al,
                                 static_cast<cudaStream_t>(stream));
 }

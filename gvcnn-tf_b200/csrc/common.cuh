@@ -248,6 +248,9 @@ int launch_pool_fuse_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
 int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
                               uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
                               float fill, int dtype, cudaStream_t st);
+int launch_pool_fuse_bwd_fast(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                              int pool, int dtype, cudaStream_t st);
 int launch_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
                          const float *weights, int64_t w_sb,
                          const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,

@@ -1,0 +1,195 @@
+// Pooling + fusion backward, fast path: V compile-time, views walked in bin order with one uniform
+// branch per view, tie bits held as one 32-bit word per descriptor element.
+//
+// Same arithmetic and op order as pool_bwd.cu (TF autodiff of nets/model.py:62-100; see there):
+//     g0 = dS / (G + V);  g1 = g0 * w_g;  max: dF_v = (1 / num_selected) * g1 | 0;  mean: dF_v = g1 / n_g.
+// Plumbing: one CTA per tile of NT*E descriptor elements of one shape.  Warp 0 ranks the views with
+// shuffles and publishes, per sorted position k, the destination row pointer of that view and, per
+// group start, the group's member mask; meanwhile every thread has its 16 bytes of dS and its
+// ceil(V/8) tie-mask words in flight.  The per-group work (num_selected = popc(ties & members), the
+// reciprocal from a shared table, two multiplies) is shared by the group's members; per view only a bit
+// test + select per element and one 128-bit streaming store remain.  Used when rows are 16-byte
+// aligned, V is one of the instantiated view counts and the reference's own group weights are wanted.
+#include "common.cuh"
+
+namespace gvcnn {
+
+struct __align__(16) BwdPlan {
+    unsigned long long rowptr[32];  // k -> byte address of row (b, view order[k]) at this tile's d0
+    uint32_t seg[32];               // at a group start k: bitmask of the group's sorted positions
+    uint32_t first_mask;            // bit k: sorted view k starts a group
+};
+
+template <typename T, int POOL, int V, int NT>
+__global__ void __launch_bounds__(NT)
+pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins, const int64_t bin_sb,
+                          const uint8_t *__restrict__ mask, const ViewPtrs gp, const int64_t g_sb, int32_t *status,
+                          const int B, const int64_t D, const int G, const int tiles_per_shape)
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr int NW = (E + 3) / 4;
+    constexpr int P = (V + 7) / 8;
+    constexpr int TD = NT * E;
+    __shared__ BwdPlan plan;
+    __shared__ float rcp_tab[V + 1];  // rcp_tab[n] = 1 / n, IEEE division
+
+    const int b = blockIdx.x / tiles_per_shape;
+    const int tile = blockIdx.x - b * tiles_per_shape;
+    const int64_t d0 = (int64_t)tile * TD;
+    const int e0 = threadIdx.x * E;
+    const bool active = (int64_t)e0 < D - d0;
+    const int64_t off = (int64_t)b * D + d0 + e0;
+
+    // ---- loads first: dS and the tie-mask planes of this thread's elements
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t pwd[P][NW];
+    if (active) {
+        raw = ldg_stream_16(dS + off);
+        if constexpr (POOL == GVCNN_POOL_MAX) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const uint8_t *mp = mask + ((int64_t)p * B) * D + off;
+                if constexpr (E == 8) {
+                    const uint2 w2 = *reinterpret_cast<const uint2 *>(mp);
+                    pwd[p][0] = w2.x;
+                    pwd[p][NW - 1] = w2.y;
+                } else {
+                    pwd[p][0] = *reinterpret_cast<const uint32_t *>(mp);
+                }
+            }
+        }
+    }
+    if (threadIdx.x <= V && threadIdx.x > 0) rcp_tab[threadIdx.x] = __fdiv_rn(1.0f, (float)threadIdx.x);
+
+    // ---- plan: warp 0 ranks the views by (bin, view)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int bin = 0x7fffffff;
+        if (lane < V) {
+            bin = __ldg(bins + (int64_t)b * bin_sb + lane);
+            if (bin < 0 || bin >= G) {
+                if (status && tile == 0) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+                bin = bin < 0 ? 0 : G - 1;
+            }
+        }
+        int below = 0, same_before = 0;
+        uint32_t peers = 0u;  // lanes (views) in my group
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int bu = __shfl_sync(0xffffffffu, bin, u);
+            below += (bu < bin);
+            same_before += (bu == bin) & (u < lane);
+            peers |= (bu == bin) ? (1u << u) : 0u;
+        }
+        const int k = below + same_before;
+        const bool first = lane < V && same_before == 0;
+        const uint32_t fm = __reduce_or_sync(0xffffffffu, first ? (1u << k) : 0u);
+        if (lane < V) {
+            // the group occupies sorted positions k - same_before .. + popc(peers) - 1
+            const int n = __popc(peers);
+            const int start = k - same_before;
+            plan.seg[k] = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << start;
+            plan.rowptr[k] = (unsigned long long)(gp.p[lane] + ((int64_t)b * g_sb + d0) * (int64_t)sizeof(T));
+        }
+        if (lane == 0) plan.first_mask = fm;
+    }
+    __syncthreads();
+    if (!active) return;
+
+    const float sumw = (float)(G + V);
+    const float rcp_sumw = __frcp_rn(sumw);
+    float t[E];
+    Elem<T>::unpack(raw, t);
+#pragma unroll
+    for (int e = 0; e < E; ++e) t[e] = div_by_rcp(t[e], sumw, rcp_sumw);  // g0 = dS / sum_w
+
+    // tie bits per element: bit k <=> sorted view k attains its group's max
+    uint32_t me[E];
+    if constexpr (POOL == GVCNN_POOL_MAX) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            me[e] = 0u;
+#pragma unroll
+            for (int p = 0; p < P; ++p) me[e] |= ((pwd[p][e >> 2] >> (8 * (e & 3))) & 0xffu) << (8 * p);
+        }
+    }
+
+    const uint32_t fm = plan.first_mask;
+    const uint32_t thread_off = (uint32_t)e0 * (uint32_t)sizeof(T);
+    float val[E];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
+            const uint32_t seg = plan.seg[k];
+            const int n = __popc(seg);
+            const float w = (float)(1 + n);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float g1 = __fmul_rn(t[e], w);
+                if constexpr (POOL == GVCNN_POOL_MAX) {
+                    const int nsel = __popc(me[e] & seg);
+                    val[e] = __fmul_rn(rcp_tab[nsel], g1);  // (1 / num_selected) * g1; nsel == 0 only for NaN
+                } else {
+                    val[e] = div_by_rcp(g1, (float)n, rcp_tab[n]);
+                }
+            }
+        }
+        float o[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if constexpr (POOL == GVCNN_POOL_MAX) o[e] = (me[e] & (1u << k)) ? val[e] : 0.0f;
+            else o[e] = val[e];
+        }
+        char *dst = reinterpret_cast<char *>(plan.rowptr[k]) + thread_off;
+        stg_stream_16(dst, Elem<T>::pack(o));
+    }
+}
+
+template <typename T, int V>
+static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                             const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int64_t D, int G, int pool,
+                             cudaStream_t st)
+{
+    constexpr int NT = 256;
+    constexpr int E = Elem<T>::kVec;
+    const int64_t td = (int64_t)NT * E;
+    const int64_t tiles = (D + td - 1) / td;
+    if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
+    const unsigned grid = (unsigned)(B * tiles);
+    if (pool == GVCNN_POOL_MAX)
+        pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MAX, V, NT><<<grid, NT, 0, st>>>(
+            static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+    else
+        pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MEAN, V, NT><<<grid, NT, 0, st>>>(
+            static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int launch_bwd_fast_t(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                             const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                             int pool, cudaStream_t st)
+{
+    if (D < 256 * Elem<T>::kVec) return -1000;
+    switch (V) {
+    case 6: return launch_bwd_fast_v<T, 6>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    case 12: return launch_bwd_fast_v<T, 12>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    case 20: return launch_bwd_fast_v<T, 20>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    default: return -1000;
+    }
+}
+
+// returns -1000 when this fast path does not apply
+int launch_pool_fuse_bwd_fast(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                              int pool, int dtype, cudaStream_t st)
+{
+    if (dtype == GVCNN_F32) {
+        if (D % 4) return -1000;
+        return launch_bwd_fast_t<float>(dS, bins, bin_sb, mask, gp, g_sb, status, B, V, D, G, pool, st);
+    }
+    if (D % 8) return -1000;
+    return launch_bwd_fast_t<__nv_bfloat16>(dS, bins, bin_sb, mask, gp, g_sb, status, B, V, D, G, pool, st);
+}
+
+}  // namespace gvcnn

@@ -145,89 +145,83 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         float acc[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[e] = 0.0f;
-        if (active) {
-            const uint32_t fm = plans[s].first_mask;
-            const uint32_t tail_skip = plans[s].tail_skip;
-            uint32_t skw[(V + 3) / 4];
+        // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
+        // in uniform registers and the per-view branches below are uniform branches
+        const uint32_t fm = __reduce_or_sync(0xffffffffu, plans[s].first_mask);
+        const uint32_t tail_skip = __reduce_or_sync(0xffffffffu, plans[s].tail_skip);
+        uint32_t skw[(V + 3) / 4];
 #pragma unroll
-            for (int i = 0; i < (V + 3) / 4; ++i) skw[i] = reinterpret_cast<const uint32_t *>(plans[s].skip)[i];
+        for (int i = 0; i < (V + 3) / 4; ++i)
+            skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plans[s].skip)[i]);
+        if (active) {
             // all V rows of this thread's column, in bin order, fetched in one batch
             uint4 raw[V];
 #pragma unroll
             for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
 
             float m[E];
+            uint32_t me[E];  // tie bits per element: bit k <=> sorted view k attains its group's max
+#pragma unroll
+            for (int e = 0; e < E; ++e) me[e] = 0u;
             int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                float x[E];
-                Elem<T>::unpack(raw[k], x);
-                if (k == 0 || ((fm >> k) & 1u)) {  // uniform: this view starts a group
-                    if (k > 0) {                   // close the previous group: acc += w_g * P_g
-                        const float w = (float)(1 + cnt);
+            for (int k = 0; k <= V; ++k) {
+                if (k == V || k == 0 || ((fm >> k) & 1u)) {  // uniform: a group ends / starts here
+                    if (k > 0) {                             // close the previous group
+                        if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+                            // its members are the cnt rows before k: compare each with the group max
+#pragma unroll
+                            for (int j = 1; j <= k; ++j) {
+                                if (j > cnt) break;
+                                float x[E];
+                                Elem<T>::unpack(raw[k - j], x);
+#pragma unroll
+                                for (int e = 0; e < E; ++e)
+                                    if (x[e] == m[e]) me[e] |= 1u << (k - j);
+                            }
+                        }
+                        const float w = (float)(1 + cnt);    // acc += w_g * P_g
 #pragma unroll
                         for (int e = 0; e < E; ++e) {
                             if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
                             acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
                         }
                     }
-                    if (fill != 0.0f) {  // empty groups in between: w = 1, P = fill
-                        const int nskip = (int)((skw[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                        for (int q = 0; q < nskip; ++q) {
+                    if (fill != 0.0f) {  // empty groups in between / after: w = 1, P = fill
+                        const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
+#pragma unroll 1
+                        for (uint32_t q = 0; q < nskip; ++q) {
 #pragma unroll
                             for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
                         }
                     }
-#pragma unroll
-                    for (int e = 0; e < E; ++e) m[e] = x[e];
-                    cnt = 1;
+                    if (k < V) {
+                        Elem<T>::unpack(raw[k], m);
+                        cnt = 1;
+                    }
                 } else {
+                    float x[E];
+                    Elem<T>::unpack(raw[k < V ? k : 0], x);
 #pragma unroll
                     for (int e = 0; e < E; ++e)
                         m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
                     ++cnt;
                 }
-                // keep the running (prefix) max of the group where the row was: at a group's last
-                // member it is the group max, which the tie sweep below needs (exact in T)
-                if constexpr (MASK && POOL == GVCNN_POOL_MAX) raw[k] = Elem<T>::pack(m);
-            }
-            {
-                const float w = (float)(1 + cnt);
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
-                    acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-                }
-                if (fill != 0.0f)
-                    for (uint32_t q = 0; q < tail_skip; ++q) {
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
-                    }
             }
             if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
-                // tie sweep, last view to first: gm = max of the group the view is in; bit k of the
-                // mask <=> view k attains it.  Rows are re-read from the slot (shared memory).
-                uint32_t pw[P][NW];
-#pragma unroll
-                for (int p = 0; p < P; ++p)
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) pw[p][i] = 0u;
-                float gm[E];
-#pragma unroll
-                for (int k = V - 1; k >= 0; --k) {
-                    const bool last = (k == V - 1) || ((fm >> (k + 1)) & 1u);
-                    if (last) Elem<T>::unpack(raw[k], gm);
-                    float x[E];
-                    Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + k * kRowStride), x);
-#pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        if (x[e] == gm[e]) pw[k >> 3][e >> 2] |= 1u << (8 * (e & 3) + (k & 7));
-                }
+                // transpose to byte planes: byte e of plane word p = bits 8p..8p+7 of me[e]
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
+                    uint32_t wd[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) {
+                        wd[i] = 0u;
+#pragma unroll
+                        for (int e = 4 * i; e < 4 * i + 4; ++e) wd[i] |= ((me[e] >> (8 * p)) & 0xffu) << (8 * (e & 3));
+                    }
                     uint8_t *mp = mask + ((int64_t)p * B) * D + out_off;
-                    if constexpr (E == 8) *reinterpret_cast<uint2 *>(mp) = make_uint2(pw[p][0], pw[p][1]);
-                    else *reinterpret_cast<uint32_t *>(mp) = pw[p][0];
+                    if constexpr (E == 8) *reinterpret_cast<uint2 *>(mp) = make_uint2(wd[0], wd[1]);
+                    else *reinterpret_cast<uint32_t *>(mp) = wd[0];
                 }
             }
         }

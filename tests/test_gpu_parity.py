@@ -142,10 +142,11 @@ def test_pool_variants_agree(model, variant, pool, B, V, D, G):
     try:
         assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
         S = model.pool_fuse(x, dev(bins), G, pool=pool)
+        S.backward(dev(dS))                     # variants 1/2: generic backward; 3: V-templated backward
+        torch.cuda.synchronize()
     finally:
         _cabi.lib().gvcnn_set_pool_variant(0)
     np.testing.assert_array_equal(S.detach().cpu().numpy(), O.pool_fuse_fwd(F, bins, G, pool, 1.0))
-    S.backward(dev(dS))
     np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
 
 
