@@ -166,6 +166,33 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------
+// Every kernel of the path is launched with programmatic stream serialization allowed: its CTAs may
+// become resident while the previous kernel on the stream drains, do their shared-memory / barrier
+// set-up, and then block in pdl_wait() until the previous kernel has completed and its writes are
+// visible.  No global memory is read or written before pdl_wait().  pdl_launch_dependents() lets
+// the NEXT kernel start the same way.  With a predecessor that never triggers, behaviour is the
+// ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- exact division with a precomputed reciprocal -----------------------------
 // a / b, correctly rounded (== __fdiv_rn(a, b)), given rcp_b = __frcp_rn(b) =
 // RN(1/b): q = RN(a * rcp_b) is within 1 ulp of a / b, the remainder r = a - b*q
@@ -228,6 +255,51 @@ template <> struct Elem<__nv_bfloat16> {
     __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
     __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
 };
+
+// ---- score epilogue (shared by score.cu and score_ring.cu) --------------------------
+// s = |x| / (1 + |x|) == sigmoid(log|x|); bin = (int)(s * G) with a float32
+// product (NumPy scalar semantics of model.py:23).  Returns the flag bits.
+__device__ __forceinline__ int score_and_bin(float x, float denom, int G, int edge_ulps, int clamp,
+                                             float &s_out, int &bin_out, bool x_is_score = false)
+{
+    const float xm = __fdiv_rn(x, denom);
+    const float ax = fabsf(xm);
+    float s = x_is_score ? x : (isinf(ax) ? 1.0f : __fdiv_rn(ax, __fadd_rn(1.0f, ax)));
+    int flags = 0;
+    int bin;
+    const float fg = (float)G;
+    if (isnan(s)) {
+        flags |= GVCNN_FLAG_NAN;
+        bin = clamp ? 0 : INT32_MIN;
+    } else {
+        bin = (int)__fmul_rn(s, fg);
+        if (edge_ulps > 0) {
+            const uint32_t bits = __float_as_uint(s);  // s in [0, 1]: ordered as integers
+            const uint32_t lo = bits > (uint32_t)edge_ulps ? bits - edge_ulps : 0u;
+            const uint32_t hi = bits + edge_ulps;
+            if ((int)__fmul_rn(__uint_as_float(lo), fg) != bin ||
+                (int)__fmul_rn(__uint_as_float(hi), fg) != bin)
+                flags |= GVCNN_FLAG_NEAR_EDGE;
+        }
+        if (bin >= G) {
+            flags |= GVCNN_FLAG_BIN_RANGE;
+            if (clamp) bin = G - 1;
+        }
+    }
+    s_out = s;
+    bin_out = bin;
+    return flags;
+}
+
+__device__ __forceinline__ void publish(int flags, int32_t *flag_out, int32_t *status)
+{
+    if (flag_out) *flag_out = flags;
+    if (status && flags) {
+        if (flags & GVCNN_FLAG_BIN_RANGE) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
+        if (flags & GVCNN_FLAG_NAN) atomicAdd(status + GVCNN_STATUS_NAN, 1);
+        if (flags & GVCNN_FLAG_NEAR_EDGE) atomicAdd(status + GVCNN_STATUS_NEAR_EDGE, 1);
+    }
+}
 
 // ---- launchers implemented in the .cu files ----------------------------------
 int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,

@@ -40,6 +40,8 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
     const bool active = (int64_t)e0 < D - d0;
     const int64_t off = (int64_t)b * D + d0 + e0;
 
+    pdl_wait();
+    pdl_launch_dependents();
     // ---- loads first: dS and the tie-mask planes of this thread's elements
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
     uint32_t pwd[P][NW];
@@ -156,12 +158,14 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
     const int64_t tiles = (D + td - 1) / td;
     if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
     const unsigned grid = (unsigned)(B * tiles);
+    cudaError_t err;
     if (pool == GVCNN_POOL_MAX)
-        pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MAX, V, NT><<<grid, NT, 0, st>>>(
-            static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+        err = launch_pdl(pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MAX, V, NT>, dim3(grid), dim3(NT), 0, st,
+                         static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
     else
-        pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MEAN, V, NT><<<grid, NT, 0, st>>>(
-            static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+        err = launch_pdl(pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MEAN, V, NT>, dim3(grid), dim3(NT), 0, st,
+                         static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+    if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
 

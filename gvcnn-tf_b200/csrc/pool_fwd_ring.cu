@@ -70,6 +70,8 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_wait();                // nothing above touches global memory
+    pdl_launch_dependents();
 
     // tile walk shared by both roles: t = blockIdx.x + it * gridDim.x, kept as (shape b, tile in shape)
     const int step_b = (int)gridDim.x / tiles_per_shape;
@@ -284,9 +286,9 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
         auto kern = pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, V, NCONS, MINB>;                              \
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (err == cudaSuccess)                                                                              \
-            kern<<<grid, NCONS + kRingProducerThreads, smem, st>>>(fp, f_sb, bins, bin_sb,                   \
-                                                                  static_cast<T *>(S), mask, status, B, D,  \
-                                                                  G, fill, (int)tps, (int)tiles, stages);   \
+            err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
+                             bin_sb, static_cast<T *>(S), mask, status, B, D, G, fill, (int)tps,             \
+                             (int)tiles, stages);                                                            \
     } while (0)
     if (pool == GVCNN_POOL_MAX) {
         if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false);

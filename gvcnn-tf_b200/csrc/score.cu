@@ -13,50 +13,6 @@
 
 namespace gvcnn {
 
-// s = |x| / (1 + |x|) == sigmoid(log|x|); bin = (int)(s * G) with a float32
-// product (NumPy scalar semantics of model.py:23).  Returns the flag bits.
-__device__ __forceinline__ int score_and_bin(float x, float denom, int G, int edge_ulps, int clamp,
-                                             float &s_out, int &bin_out, bool x_is_score = false)
-{
-    const float xm = __fdiv_rn(x, denom);
-    const float ax = fabsf(xm);
-    float s = x_is_score ? x : (isinf(ax) ? 1.0f : __fdiv_rn(ax, __fadd_rn(1.0f, ax)));
-    int flags = 0;
-    int bin;
-    const float fg = (float)G;
-    if (isnan(s)) {
-        flags |= GVCNN_FLAG_NAN;
-        bin = clamp ? 0 : INT32_MIN;
-    } else {
-        bin = (int)__fmul_rn(s, fg);
-        if (edge_ulps > 0) {
-            const uint32_t bits = __float_as_uint(s);  // s in [0, 1]: ordered as integers
-            const uint32_t lo = bits > (uint32_t)edge_ulps ? bits - edge_ulps : 0u;
-            const uint32_t hi = bits + edge_ulps;
-            if ((int)__fmul_rn(__uint_as_float(lo), fg) != bin ||
-                (int)__fmul_rn(__uint_as_float(hi), fg) != bin)
-                flags |= GVCNN_FLAG_NEAR_EDGE;
-        }
-        if (bin >= G) {
-            flags |= GVCNN_FLAG_BIN_RANGE;
-            if (clamp) bin = G - 1;
-        }
-    }
-    s_out = s;
-    bin_out = bin;
-    return flags;
-}
-
-__device__ __forceinline__ void publish(int flags, int32_t *flag_out, int32_t *status)
-{
-    if (flag_out) *flag_out = flags;
-    if (status && flags) {
-        if (flags & GVCNN_FLAG_BIN_RANGE) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
-        if (flags & GVCNN_FLAG_NAN) atomicAdd(status + GVCNN_STATUS_NAN, 1);
-        if (flags & GVCNN_FLAG_NEAR_EDGE) atomicAdd(status + GVCNN_STATUS_NEAR_EDGE, 1);
-    }
-}
-
 constexpr int kScoreWarps = 8;
 constexpr int kScoreUnroll = 8;  // 16-byte loads in flight per lane per pass
 
@@ -72,6 +28,8 @@ view_score_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict
     constexpr int E = VEC ? Elem<T>::kVec : 1;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kScoreWarps + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
     if (row >= (int64_t)B * V) return;
     const int b = (int)(row / V);
     const int v = (int)(row - (int64_t)b * V);
@@ -169,15 +127,17 @@ static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W,
 {
     const int64_t rows = (int64_t)B * V;
     const dim3 grid((unsigned)((rows + kScoreWarps - 1) / kScoreWarps)), block(kScoreWarps * 32);
+    cudaError_t err = cudaSuccess;
 #define GVCNN_LAUNCH_SCORE(VEC_, FUSE_)                                                               \
-    view_score_kernel<T, VEC_, FUSE_><<<grid, block, 0, st>>>(rp, r_sb, W, bias, x, scores, bins, flags, \
-                                                             status, B, V, C, G, edge_ulps, clamp)
+    err = launch_pdl(view_score_kernel<T, VEC_, FUSE_>, grid, block, 0, st, rp, r_sb, W, bias, x, scores, bins, \
+                     flags, status, B, V, C, G, edge_ulps, clamp)
     if (vec) {
         if (fuse_bin) GVCNN_LAUNCH_SCORE(true, true); else GVCNN_LAUNCH_SCORE(true, false);
     } else {
         if (fuse_bin) GVCNN_LAUNCH_SCORE(false, true); else GVCNN_LAUNCH_SCORE(false, false);
     }
 #undef GVCNN_LAUNCH_SCORE
+    if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
 
