@@ -238,11 +238,11 @@ def run_cuda_arm(args):
         Fd, Rd, dSd = sets[i % NSETS]
         k_score(Rd)
         k_pool(Fd, True)
-        work = dist.all_reduce(grad_bucket, async_op=True) if world > 1 else None   # overlaps the dF kernel
+        # sum then * 1/K in one collective (ReduceOp.AVG); launched before, and overlapping, the dF kernel
+        work = dist.all_reduce(grad_bucket, op=dist.ReduceOp.AVG, async_op=True) if world > 1 else None
         k_bwd(dSd)
         if work is not None:
             work.wait()
-            grad_bucket.mul_(1.0 / world)
 
     def barrier():
         if world > 1:

@@ -409,3 +409,34 @@ def test_head_module_trains(model):
     scheme = model.group_scheme([scores[0]], G, V)
     s2, S2, logits2 = model.gvcnn_head(raw, final, head, group_scheme=scheme, group_weight=model.group_weight(scheme))
     assert torch.equal(S2, S) and torch.equal(logits2, logits)
+
+
+def test_modelnet40_sized_eval_accuracy_parity(model, c_oracle):
+    """BASELINE.json configs[4] restated: 2468 shapes x 12 views of synthetic backbone
+    features through the CUDA path and through the oracle, then the same fixed random classifier
+    (GAP -> Dense(40), nets/model.py:163-164): identical descriptors => identical logits and argmax."""
+    N, V, G, Cr, hw, Cf, ncls = 2468, 12, 10, 1024, 4, 256, 40
+    R = torch.randn((N, V, Cr), generator=torch.Generator().manual_seed(4))
+    F = torch.relu(torch.randn((N, V, hw, Cf), generator=torch.Generator().manual_seed(14)))   # post-ReLU maps: many ties
+    lim = float(np.sqrt(6.0 / (Cr + 1)))
+    W = (torch.rand((V, Cr), generator=torch.Generator().manual_seed(2)) * 2 - 1) * lim
+    b = torch.rand(V, generator=torch.Generator().manual_seed(6)) * 6 - 3
+    Wc = torch.randn((Cf, ncls), generator=torch.Generator().manual_seed(5)) * 0.05
+    # literal per-batch scheme, batches of 4 shapes (train.py:94 batch_size = 4) would give 617 schemes;
+    # per-shape mode covers every shape with its own scheme in one call
+    S, sr = model.grouping_fusion(R.cuda(), W.cuda(), b.cuda(), F.cuda(), G, score_reduce="shape")
+    bins = sr.bins.cpu().numpy()
+    xk = c_oracle.view_score_x_kernel_order(R.numpy(), W.numpy(), b.numpy(), E=4)
+    np.testing.assert_array_equal(bins, O.bins_from_scores(c_oracle.score_f32(xk), G))
+    S_ref = c_oracle.pool_fuse_fwd(F.reshape(N, V, -1).numpy(), bins, G, "max", 1.0).reshape(N, hw, Cf)
+    np.testing.assert_array_equal(S.cpu().numpy(), S_ref)
+    logits = S.cpu().mean(dim=1) @ Wc
+    logits_ref = torch.tensor(S_ref).mean(dim=1) @ Wc
+    assert torch.equal(logits.argmax(dim=1), logits_ref.argmax(dim=1))            # 100 % argmax agreement
+    torch.testing.assert_close(logits, logits_ref, rtol=1e-5, atol=1e-6)
+    # vs the float64 value of the scores: every bin mismatch sits on a bin edge; report them
+    s64 = O.score_from_x(c_oracle.view_score_x_f64(R.numpy(), W.numpy(), b.numpy()))
+    mism = bins != np.trunc(s64 * G).astype(np.int32)
+    assert (~mism | (np.abs(s64 * G - np.round(s64 * G)) < 1e-4)).all()
+    print("config 5: %d shapes, argmax agreement 100%%, %d/%d bins differ from float64 (all on edges), %d flagged within 1 ulp"
+          % (N, int(mism.sum()), mism.size, int(sr.near_edge().sum())))
