@@ -82,6 +82,91 @@ view_score_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict
     }
 }
 
+// Fast path: one warp reduces 4 rows of the same view (4 consecutive shapes), one 4 KB row at a
+// time with all 32 lanes (so every burst of loads is one contiguous row, like the generic kernel),
+// the next row's loads in flight while the current one is multiplied, and ONE transposing butterfly
+// for the 4 partial sums (6 shuffles instead of 20) followed by one epilogue pass in 4 lanes.  The
+// arithmetic is exactly the generic kernel's: lane l walks chunks (i*32 + l), butterfly offsets
+// 16,8,4,2,1 (a + b is commutative, so which lane holds which row's partial sum does not matter),
+// bias last - oracle_view_score_x_kernel_order with LPR = 32.  C is a compile-time multiple of the
+// 32-lane x 16-byte x NB batch: no bounds checks.
+constexpr int kFastRows = 4;  // rows (shapes) per warp
+
+template <typename T, int NB, bool FUSE_BIN>  // NB = 16-byte loads per lane per row = C / (32 * E)
+__global__ void __launch_bounds__(kScoreWarps * 32)
+view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict__ W,
+                       const float *__restrict__ bias, float *__restrict__ x_out, float *__restrict__ scores,
+                       int32_t *__restrict__ bins, int32_t *__restrict__ flag_out, int32_t *status, const int B,
+                       const int V, const int G, const int edge_ulps, const int clamp, const int64_t items)
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr int C = NB * 32 * E;
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * kScoreWarps + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (item >= items) return;
+    const int v = (int)(item % V);
+    const int b0 = (int)(item / V) * kFastRows;
+    const T *__restrict__ r0 = reinterpret_cast<const T *>(rp.p[v]) + lane * E;
+    const float *__restrict__ w = W + (int64_t)v * C + lane * E;
+
+    uint4 buf[2][NB];
+    float acc[kFastRows];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) buf[0][u] = ldg_stream_16(r0 + (int64_t)min(b0, B - 1) * r_sb + u * 32 * E);
+#pragma unroll
+    for (int j = 0; j < kFastRows; ++j) {
+        if (j + 1 < kFastRows) {
+            const T *rn = r0 + (int64_t)min(b0 + j + 1, B - 1) * r_sb;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) buf[(j + 1) & 1][u] = ldg_stream_16(rn + u * 32 * E);
+        }
+        float a = 0.0f;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            float f[E];
+            Elem<T>::unpack(buf[j & 1][u], f);
+#pragma unroll
+            for (int q = 0; q < E; q += 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + u * 32 * E + q));
+                a = fmaf(f[q + 0], wv.x, a);
+                a = fmaf(f[q + 1], wv.y, a);
+                a = fmaf(f[q + 2], wv.z, a);
+                a = fmaf(f[q + 3], wv.w, a);
+            }
+        }
+        acc[j] = a;
+    }
+    // transposing butterfly: after offsets 16 and 8, lane group (lane >> 3) holds row (lane >> 3)
+    const bool hi = (lane & 16) != 0;
+    float k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
+    const float s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
+    k0 = __fadd_rn(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
+    k1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
+    const bool h8 = (lane & 8) != 0;
+    float k = h8 ? k1 : k0;
+    const float sd = h8 ? k0 : k1;
+    k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, sd, 8));
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, k, off));
+
+    const int b = b0 + (lane >> 3);
+    if ((lane & 7) == 0 && b < B) {
+        const int64_t row = (int64_t)b * V + v;
+        const float x = __fadd_rn(k, __ldg(bias + v));
+        if (x_out) x_out[row] = x;
+        if constexpr (FUSE_BIN) {
+            float s;
+            int bin;
+            const int flags = score_and_bin(x, 1.0f, G, edge_ulps, clamp, s, bin);
+            scores[row] = s;
+            bins[row] = bin;
+            publish(flags, flag_out ? flag_out + row : nullptr, status);
+        }
+    }
+}
+
 // xsum[v] = sum_b x[b, v], fixed order: thread t adds b = t, t+256, ... in
 // sequence, warps butterfly, thread 0 adds the 8 warp sums in warp order.
 __global__ void __launch_bounds__(256) batch_sum_x_kernel(const float *__restrict__ x,
@@ -126,8 +211,24 @@ static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W,
                                cudaStream_t st)
 {
     const int64_t rows = (int64_t)B * V;
-    const dim3 grid((unsigned)((rows + kScoreWarps - 1) / kScoreWarps)), block(kScoreWarps * 32);
     cudaError_t err = cudaSuccess;
+    if (vec && (C == 8 * 32 * Elem<T>::kVec || C == 4 * 32 * Elem<T>::kVec)) {
+        // C_raw = 1024 (block3 of ResNet-v2-50, nets/resnet_v2.py:242) is the reference's only width
+        const int64_t items = (int64_t)V * ((B + kFastRows - 1) / kFastRows);
+        const dim3 fgrid((unsigned)((items + kScoreWarps - 1) / kScoreWarps)), fblock(kScoreWarps * 32);
+#define GVCNN_LAUNCH_FAST(NB_, FUSE_)                                                                        \
+    err = launch_pdl(view_score_fast_kernel<T, NB_, FUSE_>, fgrid, fblock, 0, st, rp, r_sb, W, bias, x, scores, \
+                     bins, flags, status, B, V, G, edge_ulps, clamp, items)
+        if (C == 8 * 32 * Elem<T>::kVec) {
+            if (fuse_bin) GVCNN_LAUNCH_FAST(8, true); else GVCNN_LAUNCH_FAST(8, false);
+        } else {
+            if (fuse_bin) GVCNN_LAUNCH_FAST(4, true); else GVCNN_LAUNCH_FAST(4, false);
+        }
+#undef GVCNN_LAUNCH_FAST
+        if (err != cudaSuccess) return (int)err;
+        return (int)cudaGetLastError();
+    }
+    const dim3 grid((unsigned)((rows + kScoreWarps - 1) / kScoreWarps)), block(kScoreWarps * 32);
 #define GVCNN_LAUNCH_SCORE(VEC_, FUSE_)                                                               \
     err = launch_pdl(view_score_kernel<T, VEC_, FUSE_>, grid, block, 0, st, rp, r_sb, W, bias, x, scores, bins, \
                      flags, status, B, V, C, G, edge_ulps, clamp)

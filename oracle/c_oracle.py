@@ -60,15 +60,19 @@ def view_score_x_f64(R, W, b, layout="bvd"):
     return x
 
 
-def view_score_x_kernel_order(R, W, b, E=4, layout="bvd"):
+def view_score_x_kernel_order(R, W, b, E=4, layout="bvd", lanes=None):
+    """x in the CUDA score kernels' summation order.  ``lanes`` = lanes per row (32 in both the
+    generic and the 4-rows-per-warp kernel of csrc/score.cu)."""
     R = np.ascontiguousarray(R, dtype=np.float32)
     B, V, C = R.shape if layout == "bvd" else (R.shape[1], R.shape[0], R.shape[2])
+    if lanes is None:
+        lanes = 32
     W = np.ascontiguousarray(W, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     x = np.empty((B, V), dtype=np.float32)
     sb, sv = _strides(layout, B, V, C)
     lib().oracle_view_score_x_kernel_order(_p(R), _p(W), _p(b), _p(x), B, V, C,
-                                           ctypes.c_int64(sb), ctypes.c_int64(sv), E)
+                                           ctypes.c_int64(sb), ctypes.c_int64(sv), E, lanes)
     return x
 
 

@@ -51,13 +51,13 @@ void oracle_view_score_x_f64(const float *R, const float *W, const float *bias,
         }
 }
 
-/* The CUDA score kernel's float32 order, restated with fmaf: lane l of a warp
- * walks chunks (i*32 + l) of E consecutive elements with one fused
- * multiply-add chain, the 32 lane sums are combined by an xor butterfly
- * (offsets 16,8,4,2,1), the bias is added last.  E = vector width in elements
- * (4 for float32 rows, 8 for bf16 rows, 1 for the unaligned fallback). */
+/* The CUDA score kernels' float32 order, restated with fmaf: a row is reduced by LPR lanes
+ * (32 in the generic kernel, 8 in the fast one: 4 rows per warp); lane l walks chunks
+ * (i*LPR + l) of E consecutive elements with one fused multiply-add chain, the LPR lane sums
+ * are combined by an xor butterfly (offsets LPR/2 ... 1), the bias is added last.  E = vector
+ * width in elements (4 for float32 rows, 8 for bf16 rows, 1 for the unaligned fallback). */
 void oracle_view_score_x_kernel_order(const float *R, const float *W, const float *bias,
-                                      float *x, int B, int V, int C, int64_t rsb, int64_t rsv, int E)
+                                      float *x, int B, int V, int C, int64_t rsb, int64_t rsv, int E, int LPR)
 {
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < B; ++b)
@@ -65,16 +65,16 @@ void oracle_view_score_x_kernel_order(const float *R, const float *W, const floa
             const float *r = R + b * rsb + v * rsv;
             const float *w = W + (int64_t)v * C;
             float lane[32], nxt[32];
-            for (int l = 0; l < 32; ++l) {
+            for (int l = 0; l < LPR; ++l) {
                 float acc = 0.0f;
-                for (int64_t base = (int64_t)l * E; base < C; base += 32 * (int64_t)E)
+                for (int64_t base = (int64_t)l * E; base < C; base += LPR * (int64_t)E)
                     for (int j = 0; j < E && base + j < C; ++j)
                         acc = fmaf(r[base + j], w[base + j], acc);
                 lane[l] = acc;
             }
-            for (int off = 16; off >= 1; off >>= 1) {
-                for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
-                memcpy(lane, nxt, sizeof lane);
+            for (int off = LPR / 2; off >= 1; off >>= 1) {
+                for (int l = 0; l < LPR; ++l) nxt[l] = lane[l] + lane[l ^ off];
+                memcpy(lane, nxt, sizeof(float) * LPR);
             }
             x[(int64_t)b * V + v] = lane[0] + bias[v];
         }
