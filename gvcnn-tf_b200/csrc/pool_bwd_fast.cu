@@ -105,45 +105,85 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
 #pragma unroll
     for (int e = 0; e < E; ++e) t[e] = div_by_rcp(t[e], sumw, rcp_sumw);  // g0 = dS / sum_w
 
-    // tie bits per element: bit k <=> sorted view k attains its group's max
-    uint32_t me[E];
-    if constexpr (POOL == GVCNN_POOL_MAX) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            me[e] = 0u;
-#pragma unroll
-            for (int p = 0; p < P; ++p) me[e] |= ((pwd[p][e >> 2] >> (8 * (e & 3))) & 0xffu) << (8 * p);
-        }
-    }
-
     const uint32_t fm = plan.first_mask;
     const uint32_t thread_off = (uint32_t)e0 * (uint32_t)sizeof(T);
-    float val[E];
+
+    if constexpr (E == 8 && POOL == GVCNN_POOL_MAX) {
+        // bf16: tie bits of an element pair share a register (bits 0..15 / 16..31 = sorted views 0..15
+        // of the even / odd element; me2b covers views 16..31); the group's value is rounded to bf16 and
+        // packed once per group, each view then only masks the packed pairs.
+        uint32_t me2[4], me2b[4];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
-            const uint32_t seg = plan.seg[k];
-            const int n = __popc(seg);
-            const float w = (float)(1 + n);
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t sel = (i & 1) ? 0x7362u : 0x5140u;
+            me2[i] = __byte_perm(pwd[0][i >> 1], P > 1 ? pwd[P > 1 ? 1 : 0][i >> 1] : 0u, sel);
+            me2b[i] = P > 2 ? __byte_perm(pwd[P > 2 ? 2 : 0][i >> 1], P > 3 ? pwd[P > 3 ? 3 : 0][i >> 1] : 0u, sel) : 0u;
+        }
+        uint32_t val2[4];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
+                const uint32_t seg = plan.seg[k];
+                const float w = (float)(1 + __popc(seg));
+                float val[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint32_t half = (e & 1) ? 0xffff0000u : 0x0000ffffu;
+                    const uint32_t lo = (seg & 0xffffu) * 0x00010001u, hi = (seg >> 16) * 0x00010001u;
+                    const int nsel = __popc(me2[e >> 1] & lo & half) + (V > 16 ? __popc(me2b[e >> 1] & hi & half) : 0);
+                    val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));
+                }
+                const uint4 pk = Elem<T>::pack(val);
+                val2[0] = pk.x; val2[1] = pk.y; val2[2] = pk.z; val2[3] = pk.w;
+            }
+            uint4 o;
+            uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t bits = ((k < 16 ? me2[i] : me2b[i]) >> (k & 15)) & 0x00010001u;
+                ow[i] = val2[i] & (bits * 0xffffu);
+            }
+            stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, o);
+        }
+    } else {
+        // tie bits per element: bit k <=> sorted view k attains its group's max
+        uint32_t me[E];
+        if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const float g1 = __fmul_rn(t[e], w);
-                if constexpr (POOL == GVCNN_POOL_MAX) {
-                    const int nsel = __popc(me[e] & seg);
-                    val[e] = __fmul_rn(rcp_tab[nsel], g1);  // (1 / num_selected) * g1; nsel == 0 only for NaN
-                } else {
-                    val[e] = div_by_rcp(g1, (float)n, rcp_tab[n]);
-                }
+                me[e] = 0u;
+#pragma unroll
+                for (int p = 0; p < P; ++p) me[e] |= ((pwd[p][e >> 2] >> (8 * (e & 3))) & 0xffu) << (8 * p);
             }
         }
-        float o[E];
+        float val[E];
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if constexpr (POOL == GVCNN_POOL_MAX) o[e] = (me[e] & (1u << k)) ? val[e] : 0.0f;
-            else o[e] = val[e];
+        for (int k = 0; k < V; ++k) {
+            if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
+                const uint32_t seg = plan.seg[k];
+                const int n = __popc(seg);
+                const float w = (float)(1 + n);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float g1 = __fmul_rn(t[e], w);
+                    if constexpr (POOL == GVCNN_POOL_MAX) {
+                        const int nsel = __popc(me[e] & seg);
+                        val[e] = __fmul_rn(rcp_tab[nsel], g1);  // (1 / num_selected) * g1; nsel == 0 only for NaN
+                    } else {
+                        val[e] = div_by_rcp(g1, (float)n, rcp_tab[n]);
+                    }
+                }
+                if constexpr (POOL == GVCNN_POOL_MEAN) packed = Elem<T>::pack(val);
+            }
+            if constexpr (POOL == GVCNN_POOL_MAX) {
+                float o[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) o[e] = (me[e] & (1u << k)) ? val[e] : 0.0f;
+                packed = Elem<T>::pack(o);
+            }
+            stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, packed);
         }
-        char *dst = reinterpret_cast<char *>(plan.rowptr[k]) + thread_off;
-        stg_stream_16(dst, Elem<T>::pack(o));
     }
 }
 

@@ -34,6 +34,17 @@ struct __align__(16) RingPlan {
     uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
 };
 
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
+{
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+// 0xFFFF in each half where the bf16 values compare equal (IEEE: -0 == +0, NaN != NaN)
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b)
+{
+    return __heq2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -54,6 +65,7 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     constexpr int P = (V + 7) / 8;
     constexpr int kMaxStages = 8;
     constexpr int TD = NCONS * E;
+    constexpr bool kPackedMax = (E == 8) && (POOL == GVCNN_POOL_MAX);  // bf16 max pooling
     constexpr uint32_t kRowStride = (uint32_t)NCONS * 16u;   // bytes between sorted rows in a slot
     constexpr uint32_t kStageBytes = kRowStride * (uint32_t)V;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -155,7 +167,72 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
 #pragma unroll
         for (int i = 0; i < (V + 3) / 4; ++i)
             skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plans[s].skip)[i]);
-        if (active) {
+        if (active && kPackedMax) {
+            // bf16 max pooling: the max of bf16 values is exact in bf16, so the running group max stays
+            // packed (2 elements per register, max.bf16x2) and is widened to float32 only when a group
+            // closes.  Tie bits of an element pair share a register: bits 0..15 / 16..31 = sorted views
+            // 0..15 of the even / odd element (a second register set covers views 16..31).
+            uint4 raw[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
+            uint32_t m2[4], me2[4], me2b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) me2[i] = me2b[i] = 0u;
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k <= V; ++k) {
+                if (k == V || k == 0 || ((fm >> k) & 1u)) {
+                    if (k > 0) {
+                        if constexpr (MASK) {
+#pragma unroll
+                            for (int j = 1; j <= k; ++j) {
+                                if (j > cnt) break;
+                                const uint32_t xw[4] = {raw[k - j].x, raw[k - j].y, raw[k - j].z, raw[k - j].w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t eq = bf16x2_eq_mask(xw[i], m2[i]);
+                                    if (k - j < 16) me2[i] |= eq & (0x00010001u << ((k - j) & 15));
+                                    else me2b[i] |= eq & (0x00010001u << ((k - j) & 15));
+                                }
+                            }
+                        }
+                        float m[E];
+                        Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
+                        const float w = (float)(1 + cnt);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                    }
+                    if (fill != 0.0f) {
+                        const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
+#pragma unroll 1
+                        for (uint32_t q = 0; q < nskip; ++q) {
+#pragma unroll
+                            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                        }
+                    }
+                    if (k < V) {
+                        m2[0] = raw[k].x; m2[1] = raw[k].y; m2[2] = raw[k].z; m2[3] = raw[k].w;
+                        cnt = 1;
+                    }
+                } else {
+                    const uint4 r = raw[k < V ? k : 0];
+                    m2[0] = bf16x2_max(m2[0], r.x); m2[1] = bf16x2_max(m2[1], r.y);
+                    m2[2] = bf16x2_max(m2[2], r.z); m2[3] = bf16x2_max(m2[3], r.w);
+                    ++cnt;
+                }
+            }
+            if constexpr (MASK) {
+                // byte planes: plane p, element e -> bits 8(p&1).. of the half of me2/me2b[e >> 1]
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const uint32_t *src = (p < 2) ? me2 : me2b;
+                    const uint32_t sel = (p & 1) ? 0x7531u : 0x6420u;
+                    const uint32_t w0 = __byte_perm(src[0], src[1], sel);
+                    const uint32_t w1 = __byte_perm(src[2], src[3], sel);
+                    *reinterpret_cast<uint2 *>(mask + ((int64_t)p * B) * D + out_off) = make_uint2(w0, w1);
+                }
+            }
+        } else if (active) {
             // all V rows of this thread's column, in bin order, fetched in one batch
             uint4 raw[V];
 #pragma unroll
