@@ -1,0 +1,49 @@
+"""bench.py contract checks that need no GPU: the reference arm runs on host cores and prints one JSON
+line with the keys the driver reads; the CUDA arm refuses to run without a device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "shapes/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_cuda_arm_fails_loudly_without_a_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_algorithmic_bytes_match_baseline_md():
+    sys.path.insert(0, ROOT)
+    import bench
+    ab = bench.algorithmic_bytes(1, 12, 2048, 1024, 4)
+    assert ab["score"] == 49248 and ab["pool_fwd"] == 106496 and ab["fwd"] == 155744
+    assert ab["bwd"] == 106496 and ab["fwd_bwd"] == 262240
+    ab2 = bench.algorithmic_bytes(1, 12, 2048, 1024, 2)
+    assert ab2["fwd"] == 77920 and ab2["fwd_bwd"] == 131168
