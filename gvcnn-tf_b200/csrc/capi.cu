@@ -248,6 +248,65 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
 }
 
 // ---------------------------------------------------------------------------
+// paper mode: score-derived differentiable group weights (no reference counterpart)
+// ---------------------------------------------------------------------------
+int gvcnn_group_weight_from_scores(const float *scores, const int32_t *bins, float *weights, int rows, int V, int G,
+                                   void *stream)
+{
+    if (!scores || !bins || !weights || rows <= 0 || V <= 0 || G <= 0) return GVCNN_E_BAD_ARG;
+    return launch_group_weight_from_scores(scores, bins, weights, rows, V, G, static_cast<cudaStream_t>(stream));
+}
+
+int gvcnn_pool_fuse_bwd_weights(const void *F, const void *dS, const void *S, const int32_t *bins,
+                                int64_t bin_stride_b, const float *weights, int64_t weight_stride_b, float *dweights,
+                                int B, int V, int64_t D, int G, int pool, int f_layout, int dtype, void *stream)
+{
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc) return rc;
+    if (!dS || !S || !bins || !weights || !dweights || bin_stride_b < 0 || weight_stride_b < 0) return GVCNN_E_BAD_ARG;
+    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    ViewPtrs fp;
+    int64_t sb;
+    bool al;
+    rc = make_view_ptrs(F, f_layout, dtype, B, V, D, fp, sb, al);
+    if (rc) return rc;
+    return launch_group_weight_grad(fp, sb, dS, S, bins, bin_stride_b, weights, weight_stride_b, dweights, B, V, D, G,
+                                    pool, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int gvcnn_score_weight_bwd(const float *dweights, const int32_t *bins, const float *x, float *dx, int rows, int V,
+                           int G, void *stream)
+{
+    if (!dweights || !bins || !x || !dx || rows <= 0 || V <= 0 || G <= 0) return GVCNN_E_BAD_ARG;
+    return launch_score_weight_bwd(dweights, bins, x, dx, rows, V, G, static_cast<cudaStream_t>(stream));
+}
+
+size_t gvcnn_view_score_bwd_workspace_bytes(int V, int C) { return (size_t)GVCNN_SCORE_BWD_SLICES * V * (C + 1) * sizeof(float); }
+
+int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *dW, float *dbias, void *dR,
+                         void *workspace, size_t workspace_bytes, int B, int V, int C, int r_layout, int dtype,
+                         void *stream)
+{
+    int rc = check_dims(B, V, C, 1, dtype);
+    if (rc) return rc;
+    if (!dx || !W || !dW || !dbias || !workspace) return GVCNN_E_BAD_ARG;
+    if (workspace_bytes < gvcnn_view_score_bwd_workspace_bytes(V, C)) return GVCNN_E_WORKSPACE;
+    ViewPtrs rp, drp;
+    int64_t sb, dsb = 0;
+    bool al;
+    rc = make_view_ptrs(R, r_layout, dtype, B, V, C, rp, sb, al);
+    if (rc) return rc;
+    if (dR) {
+        rc = make_view_ptrs(dR, r_layout, dtype, B, V, C, drp, dsb, al);
+        if (rc) return rc;
+    } else {
+        drp = rp;
+    }
+    return launch_view_score_bwd(rp, sb, dx, W, dW, dbias, drp, dsb, dR ? 1 : 0, static_cast<float *>(workspace),
+                                 GVCNN_SCORE_BWD_SLICES, B, V, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------
 // host-buffer pipeline
 // ---------------------------------------------------------------------------
 namespace {

@@ -29,7 +29,7 @@ from . import _cabi as C
 __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion", "view_scores",
     "score_bin", "pool_fuse", "grouping_fusion", "GroupDescriptors", "ScoreResult",
-    "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status",
+    "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status", "grouping_fusion_paper",
 ]
 
 _POOL = {"max": C.POOL_MAX, "mean": C.POOL_MEAN}
@@ -522,6 +522,90 @@ def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_grou
     return S, sr
 
 
+# --------------------------------------------------------------------------
+# paper mode: score-derived, differentiable group weights
+# --------------------------------------------------------------------------
+class _PaperModeFn(torch.autograd.Function):
+    """S = sum_g w_g P_g / sum_g w_g with w_g = mean score of the group's views (0 for an empty group).
+    Unlike the reference (weights fed through placeholders, train.py:127-128), the gradient reaches the
+    V Dense(1) score layers: dL/dW, dL/db (and dL/dR if the raw descriptors require grad) besides dL/dF.
+    No reference counterpart - checked against float64 autograd of the same formulas."""
+
+    @staticmethod
+    def forward(ctx, W, b, G, pool, f_layout, r_layout, n_r, *tensors):
+        L = C.lib()
+        r_t, f_t = tensors[:n_r], tensors[n_r:]
+        rv = _Views(list(r_t) if r_layout == "list" else r_t[0], None if r_layout == "list" else r_layout, "R")
+        fv = _Views(list(f_t) if f_layout == "list" else f_t[0], None if f_layout == "list" else f_layout, "F")
+        sr = score_bin(list(r_t) if r_layout == "list" else r_t[0], W, b, G, score_reduce="shape",
+                       layout=None if r_layout == "list" else r_layout, edge_ulps=1, clamp=False, check=True)
+        dev = fv.device
+        weights = torch.empty((rv.B, G), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            C.check(L.gvcnn_group_weight_from_scores(_ptr(sr.scores), _ptr(sr.bins), _ptr(weights), rv.B, rv.V, G,
+                                                     _stream()), "gvcnn_group_weight_from_scores")
+        S, mask, _, _, bins_c, bstride, w_c, wstride = _pool_fuse_fwd(fv, sr.bins, G, pool, 0.0, weights,
+                                                                      want_mask=True, want_groups=False)
+        ctx.rv, ctx.fv, ctx.G, ctx.pool = rv, fv, G, pool
+        ctx.bstride, ctx.wstride = bstride, wstride
+        ctx.need_dr = any(t.requires_grad for t in r_t)
+        ctx.n_r = n_r
+        ctx.save_for_backward(W.contiguous(), sr.x, bins_c, w_c, S,
+                              mask if mask is not None else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(sr.scores, sr.bins, weights)
+        return S.reshape(fv.view_shape), sr.scores, sr.bins, weights
+
+    @staticmethod
+    def backward(ctx, dS, _ds, _db, _dw):
+        L = C.lib()
+        W, x, bins_c, w_c, S, mask = ctx.saved_tensors
+        mask = mask if mask.numel() else None
+        rv, fv, G, pool = ctx.rv, ctx.fv, ctx.G, ctx.pool
+        dS2 = dS.reshape(fv.B, fv.D).contiguous()
+        dev = dS2.device
+        dF = _pool_fuse_bwd(dS2, fv, bins_c, ctx.bstride, w_c, ctx.wstride, mask, G, pool)
+        dweights = torch.empty((fv.B, G), dtype=torch.float32, device=dev)
+        dx = torch.empty((fv.B, fv.V), dtype=torch.float32, device=dev)
+        dW = torch.empty_like(W)
+        dbias = torch.empty(rv.V, dtype=torch.float32, device=dev)
+        ws_bytes = L.gvcnn_view_score_bwd_workspace_bytes(rv.V, rv.D)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        dR_out, dR_views = (rv.empty_like() if ctx.need_dr else (None, None))
+        with torch.cuda.device(dev):
+            C.check(L.gvcnn_pool_fuse_bwd_weights(fv.arg, _ptr(dS2), _ptr(S), _ptr(bins_c), ctx.bstride, _ptr(w_c),
+                                                  ctx.wstride, _ptr(dweights), fv.B, fv.V, fv.D, G, _POOL[pool],
+                                                  fv.layout, _dtype_code(fv.dtype), _stream()),
+                    "gvcnn_pool_fuse_bwd_weights")
+            C.check(L.gvcnn_score_weight_bwd(_ptr(dweights), _ptr(bins_c), _ptr(x), _ptr(dx), fv.B, fv.V, G, _stream()),
+                    "gvcnn_score_weight_bwd")
+            C.check(L.gvcnn_view_score_bwd(rv.arg, _ptr(dx), _ptr(W), _ptr(dW), _ptr(dbias),
+                                           dR_views.arg if dR_views is not None else None, _ptr(ws), ws_bytes,
+                                           rv.B, rv.V, rv.D, rv.layout, _dtype_code(rv.dtype), _stream()),
+                    "gvcnn_view_score_bwd")
+        if dR_out is None:
+            gr = (None,) * ctx.n_r
+        else:
+            gr = tuple(dR_out) if isinstance(dR_out, list) else (dR_out,)
+        gf = tuple(dF) if isinstance(dF, list) else (dF,)
+        return (dW, dbias, None, None, None, None, None) + gr + gf
+
+
+def grouping_fusion_paper(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max", layout=None):
+    """Paper-mode grouping + fusion: group weight = mean discrimination score of the group's views, empty
+    groups vanish; differentiable w.r.t. the view descriptors AND the score FC (W, b, optionally the raw
+    descriptors).  Returns (shape_descriptor, scores, bins, weights).  Per-shape scores/bins."""
+    if isinstance(raw_view_descriptors, (list, tuple)):
+        r_t, r_lay = tuple(raw_view_descriptors), "list"
+    else:
+        r_t, r_lay = (raw_view_descriptors,), (layout or "bvd")
+    if isinstance(final_view_descriptors, (list, tuple)):
+        f_t, f_lay = tuple(final_view_descriptors), "list"
+    else:
+        f_t, f_lay = (final_view_descriptors,), (layout or "bvd")
+    _require_cuda(W, "W"), _require_cuda(b, "b")
+    return _PaperModeFn.apply(W, b, num_group, pool, f_lay, r_lay, len(r_t), *r_t, *f_t)
+
+
 class GVCNNHead(torch.nn.Module):
     """The trainable state of the path: V separate Dense(1) score layers
     (Keras defaults: glorot-uniform kernel, zero bias; nets/model.py:145 sits
@@ -529,10 +613,13 @@ class GVCNNHead(torch.nn.Module):
     average pooling (nets/model.py:163-164)."""
 
     def __init__(self, num_views, raw_channels, final_channels, num_classes, num_group=10, pool="max",
-                 empty_fill=1.0, score_reduce="batch"):
+                 empty_fill=1.0, score_reduce="batch", weight_mode="count"):
         super().__init__()
         self.num_views, self.num_group = num_views, num_group
         self.pool, self.empty_fill, self.score_reduce = pool, empty_fill, score_reduce
+        if weight_mode not in ("count", "score"):
+            raise ValueError("weight_mode: 'count' (reference, nets/model.py:28-41) or 'score' (paper mode)")
+        self.weight_mode = weight_mode
         lim = math.sqrt(6.0 / (raw_channels + 1))
         self.score_kernel = torch.nn.Parameter(torch.empty(num_views, raw_channels).uniform_(-lim, lim))
         self.score_bias = torch.nn.Parameter(torch.zeros(num_views))
@@ -546,13 +633,18 @@ class GVCNNHead(torch.nn.Module):
         final: list of V [N, h, w, C] maps or [N, V, h, w, C].  Returns
         (view_discrimination_scores, shape_descriptor, logits) like
         nets/model.py:166."""
-        S, sr = grouping_fusion(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
-                                final_view_descriptors, self.num_group, pool=self.pool,
-                                empty_fill=self.empty_fill, score_reduce=self.score_reduce,
-                                process_group=process_group, check=check)
+        if self.weight_mode == "score":
+            S, scores, _, _ = grouping_fusion_paper(raw_view_descriptors, self.score_kernel, self.score_bias,
+                                                    final_view_descriptors, self.num_group, pool=self.pool)
+        else:
+            S, sr = grouping_fusion(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
+                                    final_view_descriptors, self.num_group, pool=self.pool,
+                                    empty_fill=self.empty_fill, score_reduce=self.score_reduce,
+                                    process_group=process_group, check=check)
+            scores = sr.scores
         net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
         logits = self.classifier(net.to(self.classifier.weight.dtype))
-        return sr.scores, S, logits
+        return scores, S, logits
 
 
 def gvcnn_head(raw_view_descriptors, final_view_descriptors, head: GVCNNHead, group_scheme=None,

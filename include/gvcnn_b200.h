@@ -178,6 +178,34 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
                         int B, int V, int64_t D, int G, int pool,
                         int g_layout, int dtype, void *stream);
 
+/* --- paper mode: score-derived, differentiable group weights ---------------
+ * No counterpart in the reference (its weight is 1 + count and its score FC gets
+ * no gradient: nets/model.py:28-41, train.py:127-128).
+ *   gvcnn_group_weight_from_scores: weights[row, g] = mean of the scores of the
+ *     views in group g (0 if empty), float32 [rows, G]; feed it to
+ *     gvcnn_pool_fuse_fwd / _bwd as `weights` with empty_fill = 0.
+ *   gvcnn_pool_fuse_bwd_weights: dweights[b, g] = (<dS_b, P_{b,g}> - <dS_b, S_b>) / sum_w
+ *     (re-reads F once; P recomputed per group).
+ *   gvcnn_score_weight_bwd: dx[row, v] = dweights[row, bin_v] / n_{bin_v}
+ *     * sign(x) / (1 + |x|)^2, the chain through w_g = mean s and s = |x|/(1+|x|).
+ *   gvcnn_view_score_bwd: dW[v, :] = sum_b dx[b, v] R[b, v, :], dbias[v] = sum_b dx[b, v],
+ *     optional dR[b, v, :] = dx[b, v] W[v, :]; fixed reduction order
+ *     (GVCNN_SCORE_BWD_SLICES batch slices, ascending); workspace from
+ *     gvcnn_view_score_bwd_workspace_bytes. */
+#define GVCNN_SCORE_BWD_SLICES 32
+int gvcnn_group_weight_from_scores(const float *scores, const int32_t *bins, float *weights,
+                                   int rows, int V, int G, void *stream);
+int gvcnn_pool_fuse_bwd_weights(const void *F, const void *dS, const void *S, const int32_t *bins,
+                                int64_t bin_stride_b, const float *weights, int64_t weight_stride_b,
+                                float *dweights, int B, int V, int64_t D, int G, int pool,
+                                int f_layout, int dtype, void *stream);
+int gvcnn_score_weight_bwd(const float *dweights, const int32_t *bins, const float *x, float *dx,
+                           int rows, int V, int G, void *stream);
+size_t gvcnn_view_score_bwd_workspace_bytes(int V, int C);
+int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *dW, float *dbias,
+                         void *dR, void *workspace, size_t workspace_bytes,
+                         int B, int V, int C, int r_layout, int dtype, void *stream);
+
 /* Which forward pooling kernel the next calls use: 0 = auto (3 when it applies,
  * else 1, else 2), 1 = one tile per CTA, bulk-copy (TMA, cp.async.bulk) staged,
  * 2 = one tile per CTA, plain vector loads staged through shared memory,

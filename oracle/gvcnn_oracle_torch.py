@@ -114,3 +114,29 @@ def reference_step_cpu(F_views, R, W, b, num_group, pool="max", empty_fill=1.0):
         w[i] = 1 + int(scheme[i].sum())
     desc = view_pooling(F_views, scheme, pool=pool, empty_fill=empty_fill)
     return group_fusion(desc, w)
+
+
+def paper_mode(R, W, b, F, num_group, pool="max"):
+    """Differentiable paper-mode path (no reference counterpart), for autograd checks:
+    x = R.W + b; s = |x| / (1 + |x|); bins = trunc(float32(s) * G) (not differentiated);
+    w_g = mean score of the group's views (0 if empty); S = sum_g w_g P_g / sum_g w_g.
+    R [B,V,C], F [B,V,D]; any float dtype (use float64).  Returns (S, s, bins, w)."""
+    B, V, _ = R.shape
+    x = torch.einsum("bvc,vc->bv", R, W) + b[None, :]
+    s = torch.abs(x) / (1 + torch.abs(x))
+    bins = torch.trunc(s.detach().to(torch.float32) * num_group).to(torch.int64)
+    onehot = torch.nn.functional.one_hot(bins, num_group).to(R.dtype)          # [B, V, G]
+    cnt = onehot.sum(dim=1)                                                    # [B, G]
+    w = torch.where(cnt > 0, (onehot * s[:, :, None]).sum(dim=1) / cnt.clamp(min=1), torch.zeros_like(cnt))
+    big = torch.finfo(F.dtype).max
+    Ps = []
+    for g in range(num_group):
+        member = onehot[:, :, g] > 0                                           # [B, V]
+        if pool == "max":
+            Pg = torch.amax(torch.where(member[:, :, None], F, torch.full_like(F, -big)), dim=1)
+        else:
+            Pg = (F * member[:, :, None]).sum(dim=1) / cnt[:, g].clamp(min=1)[:, None]
+        Ps.append(torch.where((cnt[:, g] > 0)[:, None], Pg, torch.zeros_like(Pg)))
+    P = torch.stack(Ps, dim=1)                                                 # [B, G, D]
+    S = (w[:, :, None] * P).sum(dim=1) / w.sum(dim=1, keepdim=True)
+    return S, s, bins, w

@@ -440,3 +440,37 @@ def test_modelnet40_sized_eval_accuracy_parity(model, c_oracle):
     assert (~mism | (np.abs(s64 * G - np.round(s64 * G)) < 1e-4)).all()
     print("config 5: %d shapes, argmax agreement 100%%, %d/%d bins differ from float64 (all on edges), %d flagged within 1 ulp"
           % (N, int(mism.sum()), mism.size, int(sr.near_edge().sum())))
+
+
+@pytest.mark.parametrize("pool", ["max", "mean"])
+def test_paper_mode_gradients_match_float64_autograd(model, pool):
+    """SURVEY 8f n2 (parity-unpinned: the reference has no such gradient): score-derived weights, gradient
+    reaches the V Dense(1) layers.  Checked against float64 autograd of the same formulas."""
+    from oracle import gvcnn_oracle_torch as OT
+    torch.manual_seed(3)
+    B, V, Cr, D, G = 96, 12, 256, 512, 8
+    R = torch.randn(B, V, Cr)
+    W = (torch.rand(V, Cr) * 2 - 1) * float(np.sqrt(6.0 / (Cr + 1)))
+    b = torch.rand(V) * 2 - 1
+    F = torch.relu(torch.randn(B, V, D)) if pool == "max" else torch.randn(B, V, D)
+    dS = torch.randn(B, D)
+    Rd, Wd, bd, Fd = (t.cuda().requires_grad_(True) for t in (R, W, b, F))
+    S, scores, bins, w = model.grouping_fusion_paper(Rd, Wd, bd, Fd, G, pool=pool)
+    S.backward(dS.cuda())
+    R64, W64, b64, F64 = (t.double().requires_grad_(True) for t in (R, W, b, F))
+    S64, s64, bins64, w64 = OT.paper_mode(R64, W64, b64, F64, G, pool=pool)
+    S64.backward(dS.double())
+    assert torch.equal(bins.cpu().long(), bins64)
+    torch.testing.assert_close(w.cpu().double(), w64.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(S.detach().cpu().double(), S64.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(Fd.grad.cpu().double(), F64.grad, rtol=1e-5, atol=1e-6)
+    scale = float(W64.grad.abs().max())
+    torch.testing.assert_close(Wd.grad.cpu().double(), W64.grad, rtol=1e-3, atol=2e-4 * scale)
+    torch.testing.assert_close(bd.grad.cpu().double(), b64.grad, rtol=1e-3, atol=2e-4 * float(b64.grad.abs().max()))
+    torch.testing.assert_close(Rd.grad.cpu().double(), R64.grad, rtol=1e-3, atol=2e-4 * float(R64.grad.abs().max()))
+    # head in paper mode: the score FC now trains
+    head = model.GVCNNHead(V, Cr, D, 5, num_group=G, weight_mode="score").cuda()
+    scores2, S2, logits = head(R.cuda(), F.cuda().requires_grad_(True))
+    torch.nn.functional.cross_entropy(logits, torch.arange(B, device="cuda") % 5).backward()
+    assert head.score_kernel.grad is not None and torch.isfinite(head.score_kernel.grad).all()
+    assert float(head.score_kernel.grad.abs().sum()) > 0
