@@ -186,6 +186,121 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
         S[out_off] = Elem<T>::from_float(acc[0]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// View-chunked variant for many views (V > 32): the V x TD slab no longer fits next to enough CTAs,
+// so the views are streamed through shared memory in bin order, VC at a time, double-buffered: thread 0
+// fires the bulk copies of chunk c + 2 as soon as chunk c has been consumed.  Threads keep the group
+// walk's state (running max | sum, group size, accumulated fusion) in registers across chunks, so the
+// arithmetic and its order are exactly the generic kernel's.  Needs the bins before the first copy (rows
+// are placed in sorted order).  No tie mask (a group may span chunks): max-mode training with V > 32
+// takes the one-shot kernel above.
+constexpr int kChunkViews = 8;
+
+template <typename T, int POOL>
+__global__ void __launch_bounds__(256)
+pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
+                             const int64_t bin_sb, T *__restrict__ S, T *__restrict__ Pout,
+                             const float *__restrict__ weights, const int64_t w_sb, int32_t *status, const int B,
+                             const int V, const int64_t D, const int G, const float fill, const int tiles_per_shape)
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr int NT = 256;
+    constexpr int TD = NT * E;
+    constexpr uint32_t kRowStride = NT * 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [2][kChunkViews][TD]
+    __shared__ Plan plan;
+    __shared__ __align__(8) uint64_t bar[2];
+
+    const int b = blockIdx.x / tiles_per_shape;
+    const int tile = blockIdx.x - b * tiles_per_shape;
+    const int64_t d0 = (int64_t)tile * TD;
+    const int n_valid = (int)min((int64_t)TD, D - d0);
+    const int e0 = threadIdx.x * E;
+    const bool active = e0 < n_valid;
+    const float *wrow = weights ? weights + (int64_t)b * w_sb : nullptr;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    build_plan(plan, bins + (int64_t)b * bin_sb, V, G, status, wrow);  // barriers inside: also publishes bar init
+    const int nchunks = (V + kChunkViews - 1) / kChunkViews;
+    const uint32_t row_bytes = (uint32_t)n_valid * sizeof(T);
+    auto issue = [&](int c) {  // thread 0 only
+        const int k0 = c * kChunkViews;
+        const int nv = min(kChunkViews, V - k0);
+        unsigned char *dst = smem_raw + (size_t)(c & 1) * kChunkViews * kRowStride;
+        mbar_expect_tx(&bar[c & 1], row_bytes * (uint32_t)nv);
+        for (int j = 0; j < nv; ++j)
+            bulk_g2s(dst + (size_t)j * kRowStride,
+                     fp.p[plan.order[k0 + j]] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &bar[c & 1]);
+    };
+    if (threadIdx.x == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    float acc[E], m[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = m[e] = 0.0f;
+    const int64_t out_off = (int64_t)b * D + d0 + e0;
+    int prev_g = -1, cur_g = -1, len = 0;
+    float w = 0.0f;
+    auto close_group = [&]() {  // acc += w_g * P_g for the group that just ended
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)len);
+            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+        }
+        if (Pout && active) stg_stream_16(Pout + ((int64_t)cur_g * B) * D + out_off, Elem<T>::pack(m));
+        prev_g = cur_g;
+    };
+    auto skip_empty = [&](int from, int to) {  // empty groups from..to-1: w = 1 (or given), P = fill
+        for (int q = from; q < to; ++q) {
+            if (fill != 0.0f) {
+                const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+            }
+            if (Pout && active) store_fill<T, true>(Pout + ((int64_t)q * B) * D + out_off, fill);
+        }
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&bar[c & 1], (uint32_t)(c >> 1) & 1u);
+        const unsigned char *col = smem_raw + (size_t)(c & 1) * kChunkViews * kRowStride + (size_t)threadIdx.x * 16;
+        const int k0 = c * kChunkViews;
+        const int nv = min(kChunkViews, V - k0);
+        for (int j = 0; j < nv; ++j) {
+            const int k = k0 + j;
+            float x[E];
+            Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + (size_t)j * kRowStride), x);
+            const int g = plan.gbin[k];
+            if (g != cur_g) {  // uniform: view k starts a group
+                if (cur_g >= 0) close_group();
+                skip_empty(prev_g + 1, g);
+                cur_g = g;
+                len = plan.glen[k];
+                w = plan.gw[k];
+#pragma unroll
+                for (int e = 0; e < E; ++e) m[e] = x[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+            }
+        }
+        __syncthreads();  // everyone is done with this buffer
+        if (threadIdx.x == 0 && c + 2 < nchunks) issue(c + 2);
+    }
+    close_group();
+    skip_empty(prev_g + 1, G);
+    if (!active) return;
+    const float sumw = plan.sumw;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = __fdiv_rn(acc[e], sumw);
+    stg_stream_16(S + out_off, Elem<T>::pack(acc));
+}
+
 // threads per CTA: the largest of 256/128/64/32 whose slab fits ~56 KB (so >= 4
 // CTAs share an SM), but never more than one tile row needs.
 static int pick_threads(int V, int64_t D, int E, size_t elt, size_t budget)
@@ -202,6 +317,31 @@ static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
                         void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
                         bool vec, int variant, cudaStream_t st)
 {
+    if (vec && V > 32 && !(mask != nullptr && pool == GVCNN_POOL_MAX) && D >= 64 * Elem<T>::kVec) {
+        constexpr int EV = Elem<T>::kVec;
+        const int64_t tdv = 256 * EV;
+        const int64_t tilesv = (D + tdv - 1) / tdv;
+        if ((int64_t)B * tilesv > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
+        const size_t smemv = (size_t)2 * kChunkViews * 256 * 16;  // 64 KB: 3 CTAs per SM
+        cudaError_t e2;
+        if (pool == GVCNN_POOL_MAX) {
+            auto kern = pool_fuse_fwd_chunked_kernel<T, GVCNN_POOL_MAX>;
+            e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);
+            if (e2 == cudaSuccess)
+                kern<<<(unsigned)(B * tilesv), 256, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),
+                                                                static_cast<T *>(Pout), weights, w_sb, status, B, V, D,
+                                                                G, fill, (int)tilesv);
+        } else {
+            auto kern = pool_fuse_fwd_chunked_kernel<T, GVCNN_POOL_MEAN>;
+            e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);
+            if (e2 == cudaSuccess)
+                kern<<<(unsigned)(B * tilesv), 256, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),
+                                                                static_cast<T *>(Pout), weights, w_sb, status, B, V, D,
+                                                                G, fill, (int)tilesv);
+        }
+        if (e2 != cudaSuccess) return (int)e2;
+        return (int)cudaGetLastError();
+    }
     const int E = vec ? Elem<T>::kVec : 1;
     const int nt = pick_threads(V, D, E, sizeof(T), 56 * 1024);
     const size_t smem = (size_t)V * nt * E * sizeof(T);

@@ -474,3 +474,28 @@ def test_paper_mode_gradients_match_float64_autograd(model, pool):
     torch.nn.functional.cross_entropy(logits, torch.arange(B, device="cuda") % 5).backward()
     assert head.score_kernel.grad is not None and torch.isfinite(head.score_kernel.grad).all()
     assert float(head.score_kernel.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0), ("max", 0.0)])
+@pytest.mark.parametrize("B,V,D,G", [(5, 80, 2048, 8), (3, 33, 260, 7), (2, 128, 1024, 16), (4, 40, 1028, 3)])
+def test_many_views_chunked_forward(model, pool, fill, B, V, D, G):
+    """V > 32 without a tie mask (inference, or mean pooling) takes the view-chunked kernel: same bits."""
+    F, bins, dS = make_inputs(B * 7 + V, B, V, D, G, ties=True)
+    S = model.pool_fuse(dev(F), dev(bins), G, pool=pool, empty_fill=fill)
+    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, bins, G, pool, fill))
+    # per-group descriptors and caller-supplied weights go through the same kernel
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[bins[0], np.arange(V)] = 1
+    views = [dev(F[:, v]) for v in range(V)]
+    desc = model.view_pooling(views, dev(scheme), pool=pool, empty_fill=fill)
+    want = O.view_pooling([F[:, v] for v in range(V)], scheme, pool=pool, empty_fill=fill)
+    for g in (0, G - 1):
+        np.testing.assert_array_equal(desc[g].cpu().numpy(), want[g])
+    w = np.random.default_rng(V).uniform(0.5, 2.0, G).astype(np.float32)
+    S2 = model.group_fusion(desc, dev(w))
+    np.testing.assert_array_equal(S2.cpu().numpy(), O.group_fusion(want, w))
+    if pool == "mean":          # training path without a mask
+        x = dev(F).requires_grad_(True)
+        Sg = model.pool_fuse(x, dev(bins), G, pool=pool, empty_fill=fill)
+        Sg.backward(dev(dS))
+        np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
