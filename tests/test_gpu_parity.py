@@ -499,3 +499,28 @@ def test_many_views_chunked_forward(model, pool, fill, B, V, D, G):
         Sg = model.pool_fuse(x, dev(bins), G, pool=pool, empty_fill=fill)
         Sg.backward(dev(dS))
         np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
+
+
+def test_train_head_driver_learns_and_resumes(model, tmp_path):
+    """the train.py-shaped driver (same flags / LR policy / per-epoch checkpoints) trains the
+    head on synthetic features, in the reference-literal mode and in paper mode, and resumes."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_head", os.path.join(root, "gvcnn-tf_b200", "train_head.py"))
+    th = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(th)
+    common = ["--num_views", "6", "--raw_channels", "64", "--final_channels", "128", "--train_size", "48",
+              "--val_size", "24", "--batch_size", "8", "--val_batch_size", "8", "--base_learning_rate", "0.05",
+              "--training_number_of_steps", "200"]
+    for mode in ("count", "score"):
+        logdir = str(tmp_path / mode)
+        extra = ["--weight_mode", mode] + (["--score_reduce", "shape"] if mode == "score" else [])
+        h1 = th.main(common + extra + ["--how_many_training_epochs", "3", "--train_logdir", logdir])
+        assert len(h1) == 3 and h1[-1][1] < h1[0][1], "training loss should go down: %s" % h1
+        assert os.path.exists(os.path.join(logdir, "gvcnn.ckpt-0002"))
+        h2 = th.main(common + extra + ["--how_many_training_epochs", "4", "--train_logdir", logdir,
+                                       "--saved_checkpoint_dir", logdir])
+        assert [e for e, _, _ in h2] == [3]                  # resumed after epoch 2
+    fl = th.build_flags().parse_args([])
+    assert fl.num_views == 6 and fl.num_group == 10 and fl.batch_size == 4 and fl.momentum == 0.9   # train.py:94-97
+    assert abs(th.learning_rate(fl, 0) - 0.001) < 1e-12 and th.learning_rate(fl, 300000) == 0.0
