@@ -524,3 +524,46 @@ def test_train_head_driver_learns_and_resumes(model, tmp_path):
     fl = th.build_flags().parse_args([])
     assert fl.num_views == 6 and fl.num_group == 10 and fl.batch_size == 4 and fl.momentum == 0.9   # train.py:94-97
     assert abs(th.learning_rate(fl, 0) - 0.001) < 1e-12 and th.learning_rate(fl, 300000) == 0.0
+
+
+def test_real_geometry_spatial_maps(model, c_oracle):
+    """The reference's real descriptor geometry: block4 maps [N, 10, 10, 2048] per view (nets/model.py:149,
+    D = h*w*C = 204800), V = 6 views, num_group = 10, batch 4 (train.py:94-97), as a list of V tensors."""
+    N, V, G = 4, 6, 10
+    rng = np.random.default_rng(8)
+    F = rng.standard_normal((V, N, 10, 10, 2048)).astype(np.float32)
+    bins = rng.integers(0, G, V).astype(np.int32)                   # one scheme for the batch (literal mode)
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[bins, np.arange(V)] = 1
+    views = [dev(F[v]).requires_grad_(True) for v in range(V)]
+    sch = dev(scheme)
+    S = model.group_fusion(model.view_pooling(views, sch), model.group_weight(sch))
+    assert tuple(S.shape) == (N, 10, 10, 2048)
+    want = c_oracle.pool_fuse_fwd(F.reshape(V, N, -1), bins, G, "max", 1.0, layout="vbd")
+    np.testing.assert_array_equal(S.detach().cpu().numpy().reshape(N, -1), want)
+    dS = rng.standard_normal((N, 10, 10, 2048)).astype(np.float32)
+    S.backward(dev(dS))
+    wantg = c_oracle.pool_fuse_bwd(dS.reshape(N, -1), F.reshape(V, N, -1), bins, G, "max", layout="vbd")
+    got = np.stack([v.grad.cpu().numpy().reshape(N, -1) for v in views])
+    np.testing.assert_array_equal(got, wantg)
+
+
+def test_streams_are_independent(model):
+    """The C ABI is stream-ordered and re-entrant: two streams, different problems, interleaved calls."""
+    F1, b1, _ = make_inputs(1, 300, 12, 2048, 8)
+    F2, b2, _ = make_inputs(2, 200, 6, 1024, 10)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    x1, x2, bb1, bb2 = dev(F1), dev(F2), dev(b1), dev(b2)
+    torch.cuda.synchronize()
+    outs1, outs2 = [], []
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            outs1.append(model.pool_fuse(x1, bb1, 8))
+        with torch.cuda.stream(s2):
+            outs2.append(model.pool_fuse(x2, bb2, 10, pool="mean", empty_fill=0.0))
+    torch.cuda.synchronize()
+    w1, w2 = O.pool_fuse_fwd(F1, b1, 8), O.pool_fuse_fwd(F2, b2, 10, "mean", 0.0)
+    for a in outs1:
+        np.testing.assert_array_equal(a.cpu().numpy(), w1)
+    for a in outs2:
+        np.testing.assert_array_equal(a.cpu().numpy(), w2)
