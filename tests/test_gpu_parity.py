@@ -567,3 +567,34 @@ def test_streams_are_independent(model):
         np.testing.assert_array_equal(a.cpu().numpy(), w1)
     for a in outs2:
         np.testing.assert_array_equal(a.cpu().numpy(), w2)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
+@pytest.mark.parametrize("D", [1024, 2048])
+@pytest.mark.parametrize("G", [2, 4, 8, 16])
+@pytest.mark.parametrize("V", [6, 12, 20, 80])
+def test_sweep_grid_parity(model, c_oracle, V, G, D, pool, fill, dtype):
+    """Every point of BASELINE.json configs[3] (V x G x D x dtype, both pool modes) at a small batch:
+    scores/bins, fused descriptor and gradient against the oracle (exact in fp32, exact after the final
+    rounding in bf16 - i.e. well inside north_star's 1e-5 / 1e-2)."""
+    B, Cr = 24, 1024
+    F, _, dS = make_inputs(V * 1000 + G * 10 + D, B, V, D, G, ties=(G % 4 == 0))
+    R, W, b = score_inputs(V + G, B, V, Cr, bias_range=0.3)
+    if dtype == "bf16":
+        F, dS, R = O.round_bf16(F), O.round_bf16(dS), O.round_bf16(R)
+        td = torch.bfloat16
+    else:
+        td = torch.float32
+    x = dev(F, td).requires_grad_(True)
+    S, sr = model.grouping_fusion(dev(R, td), dev(W), dev(b), x, G, pool=pool, empty_fill=fill)
+    bins = sr.bins.cpu().numpy()
+    xk = c_oracle.view_score_x_kernel_order(R, W, b, E=8 if dtype == "bf16" else 4)
+    np.testing.assert_array_equal(bins, O.bins_from_scores(c_oracle.score_f32(xk), G))
+    want = c_oracle.pool_fuse_fwd(F, bins, G, pool, fill)
+    S.backward(dev(dS, td))
+    wantg = c_oracle.pool_fuse_bwd(dS, F, bins, G, pool)
+    if dtype == "bf16":
+        want, wantg = O.round_bf16(want), O.round_bf16(wantg)
+    np.testing.assert_array_equal(S.detach().float().cpu().numpy(), want)
+    np.testing.assert_array_equal(x.grad.float().cpu().numpy(), wantg)
