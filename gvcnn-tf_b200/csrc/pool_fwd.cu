@@ -188,23 +188,26 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
 
 // ---------------------------------------------------------------------------------------------
 // View-chunked variant for many views (V > 32): the V x TD slab no longer fits next to enough CTAs,
-// so the views are streamed through shared memory in bin order, VC at a time, double-buffered: thread 0
-// fires the bulk copies of chunk c + 2 as soon as chunk c has been consumed.  Threads keep the group
-// walk's state (running max | sum, group size, accumulated fusion) in registers across chunks, so the
-// arithmetic and its order are exactly the generic kernel's.  Needs the bins before the first copy (rows
-// are placed in sorted order).  No tie mask (a group may span chunks): max-mode training with V > 32
-// takes the one-shot kernel above.
+// so the views are streamed through shared memory in bin order, 8 at a time (= one tie-mask plane),
+// double-buffered: thread 0 fires the bulk copies of chunk c + 2 as soon as chunk c has been consumed.
+// Threads keep the group walk's state (running max | sum, group size, accumulated fusion) in registers
+// across chunks, so the arithmetic and its order are exactly the generic kernel's.  Needs the bins
+// before the first copy (rows are placed in sorted order).
+// Tie mask with groups that span chunks: a member's bit is set when it equals the group's running max at
+// the end of ITS chunk; if a later chunk raises the max of an element, the thread clears that element's
+// bits of the group in the planes it wrote earlier (its own bytes, read back through L2).  Bits therefore
+// end up meaning "equals the final group max", as in the one-shot kernels.
 constexpr int kChunkViews = 8;
 
-template <typename T, int POOL>
-__global__ void __launch_bounds__(256)
+template <typename T, int POOL, bool MASK, int NT>
+__global__ void __launch_bounds__(NT)
 pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
-                             const int64_t bin_sb, T *__restrict__ S, T *__restrict__ Pout,
+                             const int64_t bin_sb, T *__restrict__ S, T *__restrict__ Pout, uint8_t *__restrict__ mask,
                              const float *__restrict__ weights, const int64_t w_sb, int32_t *status, const int B,
                              const int V, const int64_t D, const int G, const float fill, const int tiles_per_shape)
 {
     constexpr int E = Elem<T>::kVec;
-    constexpr int NT = 256;
+    constexpr int NW = E / 4;
     constexpr int TD = NT * E;
     constexpr uint32_t kRowStride = NT * 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [2][kChunkViews][TD]
@@ -240,12 +243,43 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
         if (nchunks > 1) issue(1);
     }
 
-    float acc[E], m[E];
+    float acc[E], m[E], m_in[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = m[e] = 0.0f;
+    for (int e = 0; e < E; ++e) acc[e] = m[e] = m_in[e] = 0.0f;
     const int64_t out_off = (int64_t)b * D + d0 + e0;
-    int prev_g = -1, cur_g = -1, len = 0;
+    int prev_g = -1, cur_g = -1, len = 0, gs = 0;  // gs = sorted position where the open group started
     float w = 0.0f;
+    uint32_t pw[NW > 0 ? NW : 1];
+    const unsigned char *col = smem_raw;
+    int k0 = 0;
+    auto mark_members = [&](int from, int to) {  // tie bits of sorted positions [from, to) of this chunk vs m
+#pragma unroll 1
+        for (int jj = from; jj < to; ++jj) {
+            float x[E];
+            Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + (size_t)(jj - k0) * kRowStride), x);
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (x[e] == m[e]) pw[e >> 2] |= 1u << (8 * (e & 3) + (jj & 7));
+        }
+    };
+    auto fix_earlier_planes = [&]() {  // the open group started before this chunk: did its max just grow?
+        uint32_t clr[NW > 0 ? NW : 1];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) clr[i] = 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (m[e] > m_in[e]) { clr[e >> 2] |= 0xffu << (8 * (e & 3)); any = true; }
+        if (any && active) {
+            for (int p = gs >> 3; p < (k0 >> 3); ++p) {
+                const int lo = max(gs, 8 * p) & 7;                        // group's positions in plane p: lo..7
+                const uint32_t pos = (0xffu << lo) & 0xffu;
+                uint32_t *mp = reinterpret_cast<uint32_t *>(mask + ((int64_t)p * B) * D + out_off);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) mp[i] &= ~(clr[i] & (pos * 0x01010101u));
+            }
+        }
+    };
     auto close_group = [&]() {  // acc += w_g * P_g for the group that just ended
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -267,18 +301,31 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
     };
     for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&bar[c & 1], (uint32_t)(c >> 1) & 1u);
-        const unsigned char *col = smem_raw + (size_t)(c & 1) * kChunkViews * kRowStride + (size_t)threadIdx.x * 16;
-        const int k0 = c * kChunkViews;
+        col = smem_raw + (size_t)(c & 1) * kChunkViews * kRowStride + (size_t)threadIdx.x * 16;
+        k0 = c * kChunkViews;
         const int nv = min(kChunkViews, V - k0);
+        if constexpr (MASK) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) pw[i] = 0u;
+#pragma unroll
+            for (int e = 0; e < E; ++e) m_in[e] = m[e];
+        }
         for (int j = 0; j < nv; ++j) {
             const int k = k0 + j;
             float x[E];
             Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + (size_t)j * kRowStride), x);
             const int g = plan.gbin[k];
             if (g != cur_g) {  // uniform: view k starts a group
-                if (cur_g >= 0) close_group();
+                if (cur_g >= 0) {
+                    if constexpr (MASK) {
+                        mark_members(max(gs, k0), k);
+                        if (gs < k0) fix_earlier_planes();
+                    }
+                    close_group();
+                }
                 skip_empty(prev_g + 1, g);
                 cur_g = g;
+                gs = k;
                 len = plan.glen[k];
                 w = plan.gw[k];
 #pragma unroll
@@ -287,6 +334,15 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
 #pragma unroll
                 for (int e = 0; e < E; ++e)
                     m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+            }
+        }
+        if constexpr (MASK) {  // the group still open at the end of the chunk: provisional bits for its members here
+            mark_members(max(gs, k0), k0 + nv);
+            if (gs < k0) fix_earlier_planes();
+            if (active) {
+                uint32_t *mp = reinterpret_cast<uint32_t *>(mask + ((int64_t)c * B) * D + out_off);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) mp[i] = pw[i];
             }
         }
         __syncthreads();  // everyone is done with this buffer
@@ -317,28 +373,35 @@ static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
                         void *Pout, uint8_t *mask, const float *weights, int64_t w_sb, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
                         bool vec, int variant, cudaStream_t st)
 {
-    if (vec && V > 32 && !(mask != nullptr && pool == GVCNN_POOL_MAX) && D >= 64 * Elem<T>::kVec) {
+    if (vec && V > 32 && D >= 64 * Elem<T>::kVec) {
         constexpr int EV = Elem<T>::kVec;
-        const int64_t tdv = 256 * EV;
+        const int ntv = (D % (256 * EV) == 0 || D > 1024 * EV) ? 256 : 128;  // narrower CTAs when a 256-wide tile would idle
+        const int64_t tdv = (int64_t)ntv * EV;
         const int64_t tilesv = (D + tdv - 1) / tdv;
         if ((int64_t)B * tilesv > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
-        const size_t smemv = (size_t)2 * kChunkViews * 256 * 16;  // 64 KB: 3 CTAs per SM
-        cudaError_t e2;
+        const size_t smemv = (size_t)2 * kChunkViews * ntv * 16;  // 64 KB (32 KB): 3 (6) CTAs per SM
+        const bool wm = (mask != nullptr) && pool == GVCNN_POOL_MAX;
+        cudaError_t e2 = cudaSuccess;
+#define GVCNN_LAUNCH_CHUNKED_NT(POOL_, MASK_, NT_)                                                             \
+    do {                                                                                                       \
+        auto kern = pool_fuse_fwd_chunked_kernel<T, POOL_, MASK_, NT_>;                                        \
+        e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);              \
+        if (e2 == cudaSuccess)                                                                                 \
+            kern<<<(unsigned)(B * tilesv), NT_, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),       \
+                                                            static_cast<T *>(Pout), mask, weights, w_sb, status, \
+                                                            B, V, D, G, fill, (int)tilesv);                    \
+    } while (0)
+#define GVCNN_LAUNCH_CHUNKED(POOL_, MASK_)                                                                     \
+    do {                                                                                                       \
+        if (ntv == 256) GVCNN_LAUNCH_CHUNKED_NT(POOL_, MASK_, 256); else GVCNN_LAUNCH_CHUNKED_NT(POOL_, MASK_, 128); \
+    } while (0)
         if (pool == GVCNN_POOL_MAX) {
-            auto kern = pool_fuse_fwd_chunked_kernel<T, GVCNN_POOL_MAX>;
-            e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);
-            if (e2 == cudaSuccess)
-                kern<<<(unsigned)(B * tilesv), 256, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),
-                                                                static_cast<T *>(Pout), weights, w_sb, status, B, V, D,
-                                                                G, fill, (int)tilesv);
+            if (wm) GVCNN_LAUNCH_CHUNKED(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_CHUNKED(GVCNN_POOL_MAX, false);
         } else {
-            auto kern = pool_fuse_fwd_chunked_kernel<T, GVCNN_POOL_MEAN>;
-            e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);
-            if (e2 == cudaSuccess)
-                kern<<<(unsigned)(B * tilesv), 256, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),
-                                                                static_cast<T *>(Pout), weights, w_sb, status, B, V, D,
-                                                                G, fill, (int)tilesv);
+            GVCNN_LAUNCH_CHUNKED(GVCNN_POOL_MEAN, false);
         }
+#undef GVCNN_LAUNCH_CHUNKED
+#undef GVCNN_LAUNCH_CHUNKED_NT
         if (e2 != cudaSuccess) return (int)e2;
         return (int)cudaGetLastError();
     }

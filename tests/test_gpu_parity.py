@@ -222,12 +222,16 @@ def test_basic_pool_identity(model):
     np.testing.assert_array_equal(S.cpu().numpy(), F.max(axis=1))
 
 
-def test_tie_mask_matches_oracle(model):
+@pytest.mark.parametrize("B,V,D,G", [(5, 12, 1024, 8), (3, 80, 1024, 4), (2, 100, 512, 2), (3, 40, 260, 16), (4, 20, 2048, 3)])
+def test_tie_mask_matches_oracle(model, B, V, D, G):
+    """The routing aid itself (ring kernel, one-shot kernel, and the chunked kernel whose groups span
+    several planes and need the clear-earlier-planes fix-up when a later chunk raises the max)."""
     from gvcnn_tf_b200.model import _Views, _pool_fuse_fwd
-    F, bins, _ = make_inputs(4, 5, 12, 1024, 8, ties=True)
+    F, bins, _ = make_inputs(4 + V, B, V, D, G, ties=True)
+    F[:, :, 1::5] = np.sort(F[:, :, 1::5], axis=1)          # strictly growing runs: every chunk raises the max
     fv = _Views(dev(F), "bvd", "F")
-    _, mask, _, _, _, _, _, _ = _pool_fuse_fwd(fv, dev(bins), 8, "max", 1.0, None, True, False)
-    np.testing.assert_array_equal(mask.cpu().numpy(), O.tie_mask_planes(F, bins, 8))
+    _, mask, _, _, _, _, _, _ = _pool_fuse_fwd(fv, dev(bins), G, "max", 1.0, None, True, False)
+    np.testing.assert_array_equal(mask.cpu().numpy(), O.tie_mask_planes(F, bins, G))
 
 
 # ---------------------------------------------------------------- score + bin
