@@ -185,6 +185,8 @@ def run_cuda_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduce must get SM slots while the dF kernel is running: high-priority NCCL stream
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)

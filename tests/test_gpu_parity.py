@@ -602,3 +602,26 @@ def test_sweep_grid_parity(model, c_oracle, V, G, D, pool, fill, dtype):
         want, wantg = O.round_bf16(want), O.round_bf16(wantg)
     np.testing.assert_array_equal(S.detach().float().cpu().numpy(), want)
     np.testing.assert_array_equal(x.grad.float().cpu().numpy(), wantg)
+
+
+def test_cuda_graph_capture_and_replay(model):
+    """The launches (including the programmatic-dependent-launch attribute and the per-launch
+    cudaFuncSetAttribute) can be captured into a CUDA graph; replays reproduce the eager result."""
+    B, V, D, G, Cr = 64, 12, 2048, 8, 1024
+    F, _, dS = make_inputs(5, B, V, D, G, ties=True)
+    R, W, b = score_inputs(6, B, V, Cr)
+    Fd, Rd, Wd, bd = dev(F), dev(R), dev(W), dev(b)
+    S_eager, sr = model.grouping_fusion(Rd, Wd, bd, Fd, G, check=False)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        model.grouping_fusion(Rd, Wd, bd, Fd, G, check=False)          # warm-up on the capture stream
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        S_graph, sr_g = model.grouping_fusion(Rd, Wd, bd, Fd, G, check=False)
+    for _ in range(3):
+        S_graph.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(S_graph, S_eager) and torch.equal(sr_g.bins, sr.bins)
