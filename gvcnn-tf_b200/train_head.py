@@ -108,6 +108,7 @@ def main(argv=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the small all-reduce must not queue behind dF
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank if world > 1 else 0)
