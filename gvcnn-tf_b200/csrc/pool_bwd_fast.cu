@@ -216,8 +216,11 @@ static int launch_bwd_fast_t(const void *dS, const int32_t *bins, int64_t bin_sb
 {
     if (D < 256 * Elem<T>::kVec) return -1000;
     switch (V) {
+    case 4: return launch_bwd_fast_v<T, 4>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
     case 6: return launch_bwd_fast_v<T, 6>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    case 8: return launch_bwd_fast_v<T, 8>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
     case 12: return launch_bwd_fast_v<T, 12>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    case 16: return launch_bwd_fast_v<T, 16>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
     case 20: return launch_bwd_fast_v<T, 20>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
     default: return -1000;
     }

@@ -383,10 +383,14 @@ static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
                          cudaStream_t st)
 {
     // the view counts of the reference's configurations (train.py:96 default 6; BASELINE sweep 6/12/20)
+    // plus the other common multi-view rigs (4, 8, 16)
     if (D < 256 * Elem<T>::kVec) return -1000;  // tiles narrower than one consumer row: generic kernel
     switch (V) {
+    case 4: return launch_ring_v<T, 4, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
     case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 8: return launch_ring_v<T, 8, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);  // GVCNN paper: 8 / 12 views
     case 12: return launch_ring_v<T, 12, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 16: return launch_ring_v<T, 16, 256, 1>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
     case 20: return launch_ring_v<T, 20, 256, 1>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
     default: return -1000;
     }

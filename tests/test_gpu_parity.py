@@ -132,7 +132,7 @@ def test_pool_fuse_fwd_bwd_bit_exact_f32(model, pool, fill, B, V, D, G):
 @pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("pool", ["max", "mean"])
 @pytest.mark.parametrize("B,V,D,G", [(19, 12, 2048, 8), (700, 12, 2048, 8), (301, 6, 1028, 10), (150, 20, 1024, 16),
-                                       (40, 32, 520, 4)])
+                                       (40, 32, 520, 4), (90, 4, 2048, 3), (333, 8, 1024, 8), (77, 16, 2048, 10)])
 def test_pool_variants_agree(model, variant, pool, B, V, D, G):
     """One-tile-per-CTA bulk-copy staging, plain-load staging and the persistent TMA ring are the
     same function (forward, tie mask and therefore backward)."""
