@@ -52,13 +52,15 @@ int make_view_ptrs(const void *X, int layout, int dtype, int B, int V, int64_t D
     return 0;
 }
 
+// kEmptyBatch: B == 0 is a valid (empty) batch - the caller returns 0 without launching anything
+constexpr int kEmptyBatch = 12345;
 int check_dims(int B, int V, int64_t D, int G, int dtype)
 {
-    if (B <= 0 || V <= 0 || D <= 0 || G <= 0) return GVCNN_E_BAD_ARG;
+    if (B < 0 || V <= 0 || D <= 0 || G <= 0) return GVCNN_E_BAD_ARG;
     if (V > GVCNN_MAX_VIEWS) return GVCNN_E_TOO_MANY_VIEWS;
     if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
     if (dtype != GVCNN_F32 && dtype != GVCNN_BF16) return GVCNN_E_BAD_DTYPE;
-    return 0;
+    return B == 0 ? kEmptyBatch : 0;
 }
 
 bool is_aligned(const void *p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
@@ -114,7 +116,7 @@ int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float
                          int r_layout, int dtype, void *stream)
 {
     int rc = check_dims(B, V, C, 1, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!W || !bias || !x) return GVCNN_E_BAD_ARG;
     if (!is_aligned(W, 4) || !is_aligned(bias, 4) || !is_aligned(x, 4)) return GVCNN_E_MISALIGNED;
     ViewPtrs rp;
@@ -175,7 +177,7 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias, float 
                         int r_layout, int dtype, int edge_ulps, int clamp, void *stream)
 {
     int rc = check_dims(B, V, C, G, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!W || !bias || !scores || !bins || edge_ulps < 0) return GVCNN_E_BAD_ARG;
     if (!is_aligned(W, 4) || !is_aligned(bias, 4) || !is_aligned(scores, 4) || !is_aligned(bins, 4))
         return GVCNN_E_MISALIGNED;
@@ -193,7 +195,7 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
                         int f_layout, int dtype, void *stream)
 {
     int rc = check_dims(B, V, D, G, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!bins || !S || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
     if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     const size_t es = elt_size(dtype);
@@ -223,7 +225,7 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
                         int dtype, void *stream)
 {
     int rc = check_dims(B, V, D, G, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!dS || !bins || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
     if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     if (pool == GVCNN_POOL_MAX && !tie_mask) return GVCNN_E_BAD_ARG;
@@ -262,7 +264,7 @@ int gvcnn_pool_fuse_bwd_weights(const void *F, const void *dS, const void *S, co
                                 int B, int V, int64_t D, int G, int pool, int f_layout, int dtype, void *stream)
 {
     int rc = check_dims(B, V, D, G, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!dS || !S || !bins || !weights || !dweights || bin_stride_b < 0 || weight_stride_b < 0) return GVCNN_E_BAD_ARG;
     if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     ViewPtrs fp;
@@ -288,6 +290,7 @@ int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *
                          void *stream)
 {
     int rc = check_dims(B, V, C, 1, dtype);
+    if (rc == kEmptyBatch) return GVCNN_E_BAD_ARG;  // a parameter gradient over an empty batch is the caller's zeros
     if (rc) return rc;
     if (!dx || !W || !dW || !dbias || !workspace) return GVCNN_E_BAD_ARG;
     if (workspace_bytes < gvcnn_view_score_bwd_workspace_bytes(V, C)) return GVCNN_E_WORKSPACE;
@@ -349,7 +352,7 @@ int gvcnn_grouping_fusion_host(const void *R_host, const void *F_host, const flo
                                void *d_workspace, size_t workspace_bytes)
 {
     int rc = check_dims(B, V, D, G, dtype);
-    if (rc) return rc;
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (C <= 0 || chunk_shapes <= 0 || !R_host || !F_host || !W_dev || !bias_dev || !S_host || !d_workspace)
         return GVCNN_E_BAD_ARG;
     if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;

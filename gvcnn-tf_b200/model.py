@@ -81,7 +81,7 @@ class _Views:
             self.keep = views
             self.V = len(views)
             self.B = first.shape[0] if first.dim() > 0 else 1
-            self.D = int(first.numel() // max(self.B, 1))
+            self.D = int(math.prod(first.shape[1:])) if first.dim() > 0 else 1
             self.view_shape = tuple(first.shape)
             self.dtype, self.device = first.dtype, first.device
             self.layout = C.LAYOUT_PTRS
@@ -103,14 +103,14 @@ class _Views:
                 self.layout = C.LAYOUT_VBD
             else:
                 raise ValueError("layout must be 'bvd' or 'vbd'")
-            self.D = int(t.numel() // (self.B * self.V)) if self.B * self.V else 0
+            self.D = int(math.prod(t.shape[2:]))
             self.view_shape = (self.B,) + tuple(t.shape[2:])
             self.dtype, self.device = t.dtype, t.device
             self.arg = ctypes.c_void_p(t.data_ptr())
             self.kind = layout
             self.tensor = t
-        if self.B <= 0 or self.V <= 0 or self.D <= 0:
-            raise ValueError("%s: empty tensor (B=%d, V=%d, D=%d)" % (name, self.B, self.V, self.D))
+        if self.V <= 0 or self.D <= 0:          # B == 0 (an empty batch) is fine: nothing is launched
+            raise ValueError("%s: no views / empty descriptors (B=%d, V=%d, D=%d)" % (name, self.B, self.V, self.D))
         if self.V > C.MAX_VIEWS:
             raise ValueError("%s: at most %d views are supported, got %d" % (name, C.MAX_VIEWS, self.V))
 

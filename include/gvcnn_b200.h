@@ -14,6 +14,7 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - return value: 0 = ok, < 0 = GVCNN_E_* argument error (nothing was
  *     launched), > 0 = a cudaError_t from the launch;  nothing throws;
+ *     B == 0 (an empty batch) is valid everywhere and returns 0 without a launch;
  *   - there is no CPU path: a machine without an sm_100 device gets
  *     GVCNN_E_NO_DEVICE / a CUDA error, never a silent fallback;
  *   - data-dependent errors the reference raises as Python exceptions

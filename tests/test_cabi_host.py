@@ -61,7 +61,9 @@ def test_argument_errors_before_any_launch(cabi):
     p = ctypes.cast(buf, ctypes.c_void_p)
     # null pointers / bad dims / bad enums are rejected with negative codes, nothing is launched
     assert L.gvcnn_pool_fuse_fwd(None, p, 12, None, 0, p, None, None, None, 4, 12, 64, 8, 0, 1.0, 0, 0, None) == -1
-    assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 0, 12, 64, 8, 0, 1.0, 0, 0, None) == -1
+    assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 0, 12, 64, 8, 0, 1.0, 0, 0, None) == 0    # empty batch: no-op
+    assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, -1, 12, 64, 8, 0, 1.0, 0, 0, None) == -1
+    assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 4, 0, 64, 8, 0, 1.0, 0, 0, None) == -1
     assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 4, 129, 64, 8, 0, 1.0, 0, 0, None) == -4
     assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 4, 12, 64, 5000, 0, 1.0, 0, 0, None) == -5
     assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 4, 12, 64, 8, 0, 1.0, 0, 7, None) == -2

@@ -625,3 +625,43 @@ def test_cuda_graph_capture_and_replay(model):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(S_graph, S_eager) and torch.equal(sr_g.bins, sr.bins)
+
+
+def test_edge_cases_empty_ragged_extremes(model):
+    """Empty batch, ragged view lists, one group for all views, every view its own group, very many
+    groups (long runs of empty groups), a single view."""
+    G, V, D = 8, 6, 256
+    # empty batch: shapes come back empty, nothing is launched, backward is a no-op
+    x = torch.zeros((0, V, D), device="cuda", requires_grad=True)
+    S = model.pool_fuse(x, torch.zeros((0, V), dtype=torch.int32, device="cuda"), G)
+    assert tuple(S.shape) == (0, D)
+    S.sum().backward()
+    assert tuple(x.grad.shape) == (0, V, D)
+    sr = model.score_bin(torch.zeros((0, V, 64), device="cuda"), torch.zeros((V, 64), device="cuda"),
+                         torch.zeros(V, device="cuda"), G)
+    assert tuple(sr.bins.shape) == (0, V)
+    # ragged inputs are rejected like tf.stack would
+    with pytest.raises(ValueError):
+        model.pool_fuse([torch.zeros(2, 8, device="cuda"), torch.zeros(2, 9, device="cuda")],
+                        torch.zeros(2, dtype=torch.int32, device="cuda"), 4)
+    with pytest.raises(ValueError):
+        model.pool_fuse(torch.zeros(2, V, D, device="cuda"), torch.zeros((2, V + 1), dtype=torch.int32, device="cuda"), G)
+    F, _, dS = make_inputs(123, 5, V, D, G, ties=True)
+    for bins in (np.full((5, V), 3, np.int32),                                  # all views collide in one group
+                 np.tile(np.arange(V, dtype=np.int32), (5, 1)),                  # every view alone
+                 np.tile(np.arange(V, dtype=np.int32)[::-1].copy(), (5, 1))):    # ... in reverse bin order
+        xx = dev(F).requires_grad_(True)
+        out = model.pool_fuse(xx, dev(bins), G)
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), O.pool_fuse_fwd(F, bins, G))
+        out.backward(dev(dS))
+        np.testing.assert_array_equal(xx.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G))
+    # many groups: G = 1000 (beyond the ring kernel's 255) and G = 4096 (the ABI maximum), mostly empty
+    for bigG in (1000, 4096):
+        bins = np.random.default_rng(bigG).integers(0, bigG, (3, 12)).astype(np.int32)
+        Fb, _, _ = make_inputs(bigG, 3, 12, 1024, 8)
+        out = model.pool_fuse(dev(Fb), dev(bins), bigG)
+        np.testing.assert_array_equal(out.cpu().numpy(), O.pool_fuse_fwd(Fb, bins, bigG))
+    with pytest.raises(Exception):
+        model.pool_fuse(dev(Fb), dev(bins), 5000)                               # GVCNN_E_TOO_MANY_GROUPS
+    with pytest.raises(ValueError):
+        model.pool_fuse(torch.zeros(1, 129, 8, device="cuda"), torch.zeros((1, 129), dtype=torch.int32, device="cuda"), 4)
