@@ -287,6 +287,18 @@ def group_scheme(view_discrimination_score, num_group, num_views):
     return scheme[0] if rows == 1 else scheme
 
 
+def _small_to_device(x, device, dtype, name):
+    """The scheme [G, V] and the weights [G] are small HOST arrays in the reference (NumPy, fed through
+    placeholders: train.py:277-288).  Accept them as such and move them next to the descriptors; this is
+    an argument transfer of a few hundred bytes, not a CPU compute path."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype) if (not x.is_cuda or x.dtype != dtype) else x
+    try:
+        return torch.as_tensor(x).to(device=device, dtype=dtype)
+    except Exception as e:                                          # noqa: BLE001
+        raise TypeError("%s must be a tensor or array-like, got %s" % (name, type(x).__name__)) from e
+
+
 def _scheme_to_bins(g_schemes: torch.Tensor, check=True):
     _require_cuda(g_schemes, "group_scheme")
     sc = g_schemes.to(torch.int32)
@@ -306,7 +318,13 @@ def _scheme_to_bins(g_schemes: torch.Tensor, check=True):
 
 def group_weight(g_schemes):
     """weights[g] = 1 + number of views in group g.  Mirrors nets/model.py:28-41.
-    g_schemes: int CUDA tensor [G, V] (or [B, G, V]); returns float32 [G] (or [B, G])."""
+    g_schemes: int tensor [G, V] (or [B, G, V]), CUDA or - as in the reference - a host array, which is
+    moved to the current CUDA device; returns a float32 CUDA tensor [G] (or [B, G])."""
+    if not (isinstance(g_schemes, torch.Tensor) and g_schemes.is_cuda):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gvcnn_b200 needs a CUDA device: there is no CPU path")
+        g_schemes = _small_to_device(g_schemes, torch.device("cuda", torch.cuda.current_device()), torch.int32,
+                                     "g_schemes")
     bins, G = _scheme_to_bins(g_schemes)
     rows, V = bins.shape
     w = torch.empty((rows, G), dtype=torch.float32, device=bins.device)
@@ -451,6 +469,9 @@ class GroupDescriptors(dict):
     def __len__(self):
         return self._G
 
+    def __contains__(self, k):
+        return isinstance(k, int) and 0 <= k < self._G
+
     def items(self):
         self._materialise()
         return dict.items(self)
@@ -474,11 +495,14 @@ def view_pooling(final_view_descriptors, group_scheme, pool="max", empty_fill=1.
     model.py behaviour (:63,:72); pool='mean', empty_fill=0.0 is unit_test.py's.
     Returns a GroupDescriptors dict {g: pooled descriptor}.
     """
-    bins, G = _scheme_to_bins(group_scheme)
     if isinstance(final_view_descriptors, (list, tuple)):
         views, lay = tuple(final_view_descriptors), "list"
     else:
         views, lay = (final_view_descriptors,), (layout or "bvd")
+    if len(views) == 0:
+        raise ValueError("final_view_descriptors: empty view list")
+    _require_cuda(views[0], "final_view_descriptors")
+    bins, G = _scheme_to_bins(_small_to_device(group_scheme, views[0].device, torch.int32, "group_scheme"))
     return GroupDescriptors(views, lay, bins, G, pool, empty_fill)
 
 
@@ -493,7 +517,7 @@ def group_fusion(group_descriptors, group_weight):
     if not isinstance(group_descriptors, GroupDescriptors):
         raise TypeError("group_fusion expects the GroupDescriptors returned by view_pooling")
     gd = group_descriptors
-    _require_cuda(group_weight, "group_weight")
+    group_weight = _small_to_device(group_weight, gd._bins.device, torch.float32, "group_weight")
     S, _ = _PoolFuseFn.apply(gd._bins, group_weight, gd._G, gd._pool, gd._fill, gd._layout,
                              len(gd._views), *gd._views)
     return S

@@ -665,3 +665,19 @@ def test_edge_cases_empty_ragged_extremes(model):
         model.pool_fuse(dev(Fb), dev(bins), 5000)                               # GVCNN_E_TOO_MANY_GROUPS
     with pytest.raises(ValueError):
         model.pool_fuse(torch.zeros(1, 129, 8, device="cuda"), torch.zeros((1, 129), dtype=torch.int32, device="cuda"), 4)
+
+
+def test_reference_style_host_arrays_for_scheme_and_weight(model, golden_dir):
+    """In the reference the scheme and the weights are NumPy arrays (train.py:277-288); the mirror takes
+    them as such (a few hundred bytes moved to the device) next to CUDA view tensors."""
+    z = np.load(os.path.join(golden_dir, "ref_graph_pool_fuse.npz"))
+    F, scheme, w, S = (z["rand_v12__%s" % k] for k in ("F", "scheme", "w", "S"))
+    views = [dev(F[v]) for v in range(F.shape[0])]
+    wd = model.group_weight(scheme)                                  # numpy in
+    np.testing.assert_array_equal(wd.cpu().numpy(), w)
+    desc = model.view_pooling(views, scheme)                         # numpy scheme
+    assert len(desc) == scheme.shape[0] and 3 in desc and 99 not in desc
+    np.testing.assert_array_equal(model.group_fusion(desc, w).cpu().numpy(), S)          # numpy weights
+    np.testing.assert_array_equal(model.group_fusion(desc, torch.tensor(w)).cpu().numpy(), S)   # CPU tensor
+    with pytest.raises(RuntimeError):
+        model.view_pooling([torch.tensor(F[v]) for v in range(F.shape[0])], scheme)      # descriptors must be CUDA
