@@ -40,6 +40,8 @@ SIGNATURES = {
                                  _i, _i, _i64, _i, _i, _f, _i, _i, _vp]),
     "gvcnn_pool_fuse_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp,
                                  _i, _i, _i64, _i, _i, _i, _i, _vp]),
+    "gvcnn_grouping_fusion_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_group_weight_from_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gvcnn_pool_fuse_bwd_weights": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_score_weight_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -2,6 +2,7 @@
 // argument validation, layout -> per-view pointer table, kernel launches, and
 // the chunked host-buffer pipeline.  Nothing here touches torch.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -247,6 +248,38 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     }
     return launch_pool_fuse_bwd(dS, bins, bin_stride_b, tie_mask, weights, weight_stride_b, gp, sb, status, B, V, D, G, pool, dtype, al,
                                 static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------
+// whole forward in one call: score + bin, then pool + fuse, chained with programmatic dependent launch
+// ---------------------------------------------------------------------------
+int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, const void *F, float *x,
+                              float *scores, int32_t *bins, int32_t *flags, void *S, uint8_t *tie_mask,
+                              int32_t *status, int B, int V, int C, int64_t D, int G, int pool, float empty_fill,
+                              int r_layout, int f_layout, int dtype, int edge_ulps, int clamp, void *stream)
+{
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
+    if (C <= 0 || !W || !bias || !scores || !bins || !S || edge_ulps < 0) return GVCNN_E_BAD_ARG;
+    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    const size_t es = elt_size(dtype);
+    ViewPtrs rp, fp;
+    int64_t rsb, fsb;
+    bool ral, fal;
+    rc = make_view_ptrs(R, r_layout, dtype, B, V, C, rp, rsb, ral);
+    if (rc) return rc;
+    rc = make_view_ptrs(F, f_layout, dtype, B, V, D, fp, fsb, fal);
+    if (rc) return rc;
+    (void)es;
+    // Two launches chained with programmatic dependent launch.  A single persistent kernel streaming R and F
+    // through one TMA ring was built and measured this round: 104.4 us alone vs 99.3 us for this chain
+    // (profiles/r01w_experiment_fused_fwd_kernel.json) - the R phase keeps fewer bytes in flight - so it was
+    // dropped.
+    rc = gvcnn_score_bin_fwd(R, W, bias, x, scores, bins, flags, status, B, V, C, G, r_layout, dtype, edge_ulps, clamp,
+                             stream);
+    if (rc) return rc;
+    return gvcnn_pool_fuse_fwd(F, bins, V, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
+                               f_layout, dtype, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -20,35 +20,9 @@
 // other case takes the generic kernel in pool_fwd.cu.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "ring_common.cuh"
 
 namespace gvcnn {
-
-constexpr int kRingProducerThreads = 32;
-
-// Per-slot plan written by the producer warp, read by the consumers.
-struct __align__(16) RingPlan {
-    uint32_t first_mask;  // bit k: the k-th sorted view starts a group
-    uint32_t tail_skip;   // empty groups after the last non-empty one
-    uint32_t pad[2];
-    uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
-};
-
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
-{
-    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
-    return *reinterpret_cast<const uint32_t *>(&r);
-}
-// 0xFFFF in each half where the bf16 values compare equal (IEEE: -0 == +0, NaN != NaN)
-__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b)
-{
-    return __heq2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // V and the consumer count are compile-time: rows sit at immediate offsets, every loop over views is
 // fully unrolled, and the only data-dependent control flow left is one uniform branch per view
@@ -157,153 +131,7 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         mbar_wait(&full_bar[s], ph);
 
         float acc[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) acc[e] = 0.0f;
-        // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
-        // in uniform registers and the per-view branches below are uniform branches
-        const uint32_t fm = __reduce_or_sync(0xffffffffu, plans[s].first_mask);
-        const uint32_t tail_skip = __reduce_or_sync(0xffffffffu, plans[s].tail_skip);
-        uint32_t skw[(V + 3) / 4];
-#pragma unroll
-        for (int i = 0; i < (V + 3) / 4; ++i)
-            skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plans[s].skip)[i]);
-        if (active && kPackedMax) {
-            // bf16 max pooling: the max of bf16 values is exact in bf16, so the running group max stays
-            // packed (2 elements per register, max.bf16x2) and is widened to float32 only when a group
-            // closes.  Tie bits of an element pair share a register: bits 0..15 / 16..31 = sorted views
-            // 0..15 of the even / odd element (a second register set covers views 16..31).
-            uint4 raw[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
-            uint32_t m2[4], me2[4], me2b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) me2[i] = me2b[i] = 0u;
-            int cnt = 0;
-#pragma unroll
-            for (int k = 0; k <= V; ++k) {
-                if (k == V || k == 0 || ((fm >> k) & 1u)) {
-                    if (k > 0) {
-                        if constexpr (MASK) {
-#pragma unroll
-                            for (int j = 1; j <= k; ++j) {
-                                if (j > cnt) break;
-                                const uint32_t xw[4] = {raw[k - j].x, raw[k - j].y, raw[k - j].z, raw[k - j].w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const uint32_t eq = bf16x2_eq_mask(xw[i], m2[i]);
-                                    if (k - j < 16) me2[i] |= eq & (0x00010001u << ((k - j) & 15));
-                                    else me2b[i] |= eq & (0x00010001u << ((k - j) & 15));
-                                }
-                            }
-                        }
-                        float m[E];
-                        Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
-                        const float w = (float)(1 + cnt);
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-                    }
-                    if (fill != 0.0f) {
-                        const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
-#pragma unroll 1
-                        for (uint32_t q = 0; q < nskip; ++q) {
-#pragma unroll
-                            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
-                        }
-                    }
-                    if (k < V) {
-                        m2[0] = raw[k].x; m2[1] = raw[k].y; m2[2] = raw[k].z; m2[3] = raw[k].w;
-                        cnt = 1;
-                    }
-                } else {
-                    const uint4 r = raw[k < V ? k : 0];
-                    m2[0] = bf16x2_max(m2[0], r.x); m2[1] = bf16x2_max(m2[1], r.y);
-                    m2[2] = bf16x2_max(m2[2], r.z); m2[3] = bf16x2_max(m2[3], r.w);
-                    ++cnt;
-                }
-            }
-            if constexpr (MASK) {
-                // byte planes: plane p, element e -> bits 8(p&1).. of the half of me2/me2b[e >> 1]
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const uint32_t *src = (p < 2) ? me2 : me2b;
-                    const uint32_t sel = (p & 1) ? 0x7531u : 0x6420u;
-                    const uint32_t w0 = __byte_perm(src[0], src[1], sel);
-                    const uint32_t w1 = __byte_perm(src[2], src[3], sel);
-                    *reinterpret_cast<uint2 *>(mask + ((int64_t)p * B) * D + out_off) = make_uint2(w0, w1);
-                }
-            }
-        } else if (active) {
-            // all V rows of this thread's column, in bin order, fetched in one batch
-            uint4 raw[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
-
-            float m[E];
-            uint32_t me[E];  // tie bits per element: bit k <=> sorted view k attains its group's max
-#pragma unroll
-            for (int e = 0; e < E; ++e) me[e] = 0u;
-            int cnt = 0;
-#pragma unroll
-            for (int k = 0; k <= V; ++k) {
-                if (k == V || k == 0 || ((fm >> k) & 1u)) {  // uniform: a group ends / starts here
-                    if (k > 0) {                             // close the previous group
-                        if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
-                            // its members are the cnt rows before k: compare each with the group max
-#pragma unroll
-                            for (int j = 1; j <= k; ++j) {
-                                if (j > cnt) break;
-                                float x[E];
-                                Elem<T>::unpack(raw[k - j], x);
-#pragma unroll
-                                for (int e = 0; e < E; ++e)
-                                    if (x[e] == m[e]) me[e] |= 1u << (k - j);
-                            }
-                        }
-                        const float w = (float)(1 + cnt);    // acc += w_g * P_g
-#pragma unroll
-                        for (int e = 0; e < E; ++e) {
-                            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
-                            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-                        }
-                    }
-                    if (fill != 0.0f) {  // empty groups in between / after: w = 1, P = fill
-                        const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
-#pragma unroll 1
-                        for (uint32_t q = 0; q < nskip; ++q) {
-#pragma unroll
-                            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
-                        }
-                    }
-                    if (k < V) {
-                        Elem<T>::unpack(raw[k], m);
-                        cnt = 1;
-                    }
-                } else {
-                    float x[E];
-                    Elem<T>::unpack(raw[k < V ? k : 0], x);
-#pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
-                    ++cnt;
-                }
-            }
-            if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
-                // transpose to byte planes: byte e of plane word p = bits 8p..8p+7 of me[e]
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    uint32_t wd[NW];
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) {
-                        wd[i] = 0u;
-#pragma unroll
-                        for (int e = 4 * i; e < 4 * i + 4; ++e) wd[i] |= ((me[e] >> (8 * p)) & 0xffu) << (8 * (e & 3));
-                    }
-                    uint8_t *mp = mask + ((int64_t)p * B) * D + out_off;
-                    if constexpr (E == 8) *reinterpret_cast<uint2 *>(mp) = make_uint2(wd[0], wd[1]);
-                    else *reinterpret_cast<uint32_t *>(mp) = wd[0];
-                }
-            }
-        }
+        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc);
         // every lane of the warp is done reading the slot: hand it back to the producer
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);

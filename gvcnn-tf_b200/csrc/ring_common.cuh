@@ -1,0 +1,199 @@
+// Shared pieces of the persistent TMA-ring kernel (pool_fwd_ring.cu): plan, packed-bf16 helpers, and the
+// per-thread tile consumer.
+#pragma once
+
+#include "common.cuh"
+
+namespace gvcnn {
+
+constexpr int kRingProducerThreads = 32;
+
+// Per-slot plan written by the producer warp, read by the consumers.
+struct __align__(16) RingPlan {
+    uint32_t first_mask;  // bit k: the k-th sorted view starts a group
+    uint32_t tail_skip;   // empty groups after the last non-empty one
+    uint32_t pad[2];
+    uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
+};
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
+{
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+// 0xFFFF in each half where the bf16 values compare equal (IEEE: -0 == +0, NaN != NaN)
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b)
+{
+    return __heq2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One consumer thread's work on one tile: its 16-byte column of the V sorted rows in a ring slot ->
+// acc[] = sum_g w_g * P_g (+ empty-group fills), in the reference's op order, and (MASK) the tie planes.
+// `plan` lives in shared memory; ROWSTRIDE = bytes between sorted rows.  Returns with acc NOT yet divided
+// by sum_w, so the caller can release the slot before the division and the store.
+template <typename T, int POOL, bool MASK, int V, uint32_t ROWSTRIDE>
+__device__ __forceinline__ void ring_consume_tile(const unsigned char *col, const RingPlan &plan_s, const float fill,
+                                                  const bool active, uint8_t *__restrict__ mask, const int B,
+                                                  const int64_t D, const int64_t out_off,
+                                                  float (&acc)[Elem<T>::kVec])
+{
+    constexpr int E = Elem<T>::kVec;
+    constexpr int NW = (E + 3) / 4;
+    constexpr int P = (V + 7) / 8;
+    constexpr uint32_t kRowStride = ROWSTRIDE;
+    constexpr bool kPackedMax = (E == 8) && (POOL == GVCNN_POOL_MAX);  // bf16 max pooling
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+    // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
+    // in uniform registers and the per-view branches below are uniform branches
+    const uint32_t fm = __reduce_or_sync(0xffffffffu, plan_s.first_mask);
+    const uint32_t tail_skip = __reduce_or_sync(0xffffffffu, plan_s.tail_skip);
+    uint32_t skw[(V + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (V + 3) / 4; ++i)
+        skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plan_s.skip)[i]);
+    if (active && kPackedMax) {
+        // bf16 max pooling: the max of bf16 values is exact in bf16, so the running group max stays
+        // packed (2 elements per register, max.bf16x2) and is widened to float32 only when a group
+        // closes.  Tie bits of an element pair share a register: bits 0..15 / 16..31 = sorted views
+        // 0..15 of the even / odd element (a second register set covers views 16..31).
+        uint4 raw[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
+        uint32_t m2[4], me2[4], me2b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) me2[i] = me2b[i] = 0u;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k <= V; ++k) {
+            if (k == V || k == 0 || ((fm >> k) & 1u)) {
+                if (k > 0) {
+                    if constexpr (MASK) {
+#pragma unroll
+                        for (int j = 1; j <= k; ++j) {
+                            if (j > cnt) break;
+                            const uint32_t xw[4] = {raw[k - j].x, raw[k - j].y, raw[k - j].z, raw[k - j].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t eq = bf16x2_eq_mask(xw[i], m2[i]);
+                                if (k - j < 16) me2[i] |= eq & (0x00010001u << ((k - j) & 15));
+                                else me2b[i] |= eq & (0x00010001u << ((k - j) & 15));
+                            }
+                        }
+                    }
+                    float m[E];
+                    Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
+                    const float w = (float)(1 + cnt);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                }
+                if (fill != 0.0f) {
+                    const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
+#pragma unroll 1
+                    for (uint32_t q = 0; q < nskip; ++q) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                    }
+                }
+                if (k < V) {
+                    m2[0] = raw[k].x; m2[1] = raw[k].y; m2[2] = raw[k].z; m2[3] = raw[k].w;
+                    cnt = 1;
+                }
+            } else {
+                const uint4 r = raw[k < V ? k : 0];
+                m2[0] = bf16x2_max(m2[0], r.x); m2[1] = bf16x2_max(m2[1], r.y);
+                m2[2] = bf16x2_max(m2[2], r.z); m2[3] = bf16x2_max(m2[3], r.w);
+                ++cnt;
+            }
+        }
+        if constexpr (MASK) {
+            // byte planes: plane p, element e -> bits 8(p&1).. of the half of me2/me2b[e >> 1]
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const uint32_t *src = (p < 2) ? me2 : me2b;
+                const uint32_t sel = (p & 1) ? 0x7531u : 0x6420u;
+                const uint32_t w0 = __byte_perm(src[0], src[1], sel);
+                const uint32_t w1 = __byte_perm(src[2], src[3], sel);
+                *reinterpret_cast<uint2 *>(mask + ((int64_t)p * B) * D + out_off) = make_uint2(w0, w1);
+            }
+        }
+    } else if (active) {
+        // all V rows of this thread's column, in bin order, fetched in one batch
+        uint4 raw[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw[k] = *reinterpret_cast<const uint4 *>(col + k * kRowStride);
+
+        float m[E];
+        uint32_t me[E];  // tie bits per element: bit k <=> sorted view k attains its group's max
+#pragma unroll
+        for (int e = 0; e < E; ++e) me[e] = 0u;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k <= V; ++k) {
+            if (k == V || k == 0 || ((fm >> k) & 1u)) {  // uniform: a group ends / starts here
+                if (k > 0) {                             // close the previous group
+                    if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+                        // its members are the cnt rows before k: compare each with the group max
+#pragma unroll
+                        for (int j = 1; j <= k; ++j) {
+                            if (j > cnt) break;
+                            float x[E];
+                            Elem<T>::unpack(raw[k - j], x);
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                                if (x[e] == m[e]) me[e] |= 1u << (k - j);
+                        }
+                    }
+                    const float w = (float)(1 + cnt);    // acc += w_g * P_g
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
+                        acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                    }
+                }
+                if (fill != 0.0f) {  // empty groups in between / after: w = 1, P = fill
+                    const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
+#pragma unroll 1
+                    for (uint32_t q = 0; q < nskip; ++q) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                    }
+                }
+                if (k < V) {
+                    Elem<T>::unpack(raw[k], m);
+                    cnt = 1;
+                }
+            } else {
+                float x[E];
+                Elem<T>::unpack(raw[k < V ? k : 0], x);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+                ++cnt;
+            }
+        }
+        if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+            // transpose to byte planes: byte e of plane word p = bits 8p..8p+7 of me[e]
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                uint32_t wd[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    wd[i] = 0u;
+#pragma unroll
+                    for (int e = 4 * i; e < 4 * i + 4; ++e) wd[i] |= ((me[e] >> (8 * p)) & 0xffu) << (8 * (e & 3));
+                }
+                uint8_t *mp = mask + ((int64_t)p * B) * D + out_off;
+                if constexpr (E == 8) *reinterpret_cast<uint2 *>(mp) = make_uint2(wd[0], wd[1]);
+                else *reinterpret_cast<uint32_t *>(mp) = wd[0];
+            }
+        }
+    }
+}
+
+}  // namespace gvcnn

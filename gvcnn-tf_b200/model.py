@@ -534,12 +534,81 @@ def basic_pool(final_view_descriptors, layout=None):
                      group_weight=w)
 
 
+class _FusedFwdFn(torch.autograd.Function):
+    """Per-shape scores + bins + pooling + fusion through gvcnn_grouping_fusion_fwd (two launches chained
+    with programmatic dependent launch, no host hop); backward = the pooling/fusion backward (dF only, as
+    in the reference)."""
+
+    @staticmethod
+    def forward(ctx, W, b, G, pool, empty_fill, f_layout, r_layout, n_r, edge_ulps, clamp, *tensors):
+        L = C.lib()
+        r_t, f_t = tensors[:n_r], tensors[n_r:]
+        rv = _Views(list(r_t) if r_layout == "list" else r_t[0], None if r_layout == "list" else r_layout, "R")
+        fv = _Views(list(f_t) if f_layout == "list" else f_t[0], None if f_layout == "list" else f_layout, "F")
+        if (rv.B, rv.V) != (fv.B, fv.V) or rv.dtype != fv.dtype:
+            raise ValueError("raw and final view descriptors must agree in batch, views and dtype")
+        dev = fv.device
+        Wc, bc = W.contiguous(), b.contiguous()
+        x = torch.empty((fv.B, fv.V), dtype=torch.float32, device=dev)
+        scores = torch.empty_like(x)
+        bins = torch.empty((fv.B, fv.V), dtype=torch.int32, device=dev)
+        flags = torch.empty_like(bins)
+        status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+        S = torch.empty((fv.B, fv.D), dtype=fv.dtype, device=dev)
+        need_grad = any(t.requires_grad for t in f_t)
+        mask = None
+        if need_grad and pool == "max":
+            mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            C.check(L.gvcnn_grouping_fusion_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(x), _ptr(scores), _ptr(bins),
+                                                _ptr(flags), _ptr(S), _ptr(mask), _ptr(status), fv.B, fv.V, rv.D, fv.D,
+                                                G, _POOL[pool], ctypes.c_float(empty_fill), rv.layout, fv.layout,
+                                                _dtype_code(fv.dtype), edge_ulps, int(clamp), _stream()),
+                    "gvcnn_grouping_fusion_fwd")
+        ctx.fv, ctx.G, ctx.pool, ctx.n_r = fv, G, pool, n_r
+        ctx.save_for_backward(bins, mask if mask is not None else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(x, scores, bins, flags, status)
+        return S.reshape(fv.view_shape), x, scores, bins, flags, status
+
+    @staticmethod
+    def backward(ctx, dS, *_unused):
+        bins, mask = ctx.saved_tensors
+        mask = mask if mask.numel() else None
+        fv = ctx.fv
+        if mask is not None:
+            # the forward clamps out-of-range bins for pooling; the saved bins may hold the raw value
+            bins = bins.clamp(0, ctx.G - 1)
+        out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins, fv.V if fv.B > 1 else 0, None, 0, mask, ctx.G, ctx.pool)
+        gf = tuple(out) if isinstance(out, list) else (out,)
+        return (None,) * 10 + (None,) * ctx.n_r + gf
+
+
 def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max",
                     empty_fill=1.0, score_reduce="shape", layout=None, clamp=False, check=True,
                     process_group=None, edge_ulps=1):
-    """The whole hot path in two launches, no host hop (replaces the
-    partial_run split of train.py:264-288): score + bin, then pool + fuse.
+    """The whole hot path with no host hop (replaces the partial_run split of
+    train.py:264-288): per-shape mode is one call into the library (score + bin,
+    then pool + fuse, chained on the device); the literal batch-mean mode needs
+    the cross-shape mean first and runs the stages separately.
     Returns (shape_descriptor, ScoreResult)."""
+    if score_reduce == "shape":
+        if isinstance(raw_view_descriptors, (list, tuple)):
+            r_t, r_lay = tuple(raw_view_descriptors), "list"
+        else:
+            r_t, r_lay = (raw_view_descriptors,), (layout or "bvd")
+        if isinstance(final_view_descriptors, (list, tuple)):
+            f_t, f_lay = tuple(final_view_descriptors), "list"
+        else:
+            f_t, f_lay = (final_view_descriptors,), (layout or "bvd")
+        _require_cuda(W, "W"), _require_cuda(b, "b")
+        if W.dtype != torch.float32 or b.dtype != torch.float32:
+            raise TypeError("W and b must be float32")
+        S, x, scores, bins, flags, status = _FusedFwdFn.apply(W, b, num_group, pool, empty_fill, f_lay, r_lay,
+                                                              len(r_t), edge_ulps, clamp, *r_t, *f_t)
+        sr = ScoreResult(x, scores, bins, flags, status, num_group)
+        if check:
+            sr.check()
+        return S, sr
     sr = score_bin(raw_view_descriptors, W, b, num_group, score_reduce=score_reduce, layout=layout,
                    edge_ulps=edge_ulps, clamp=clamp, check=check, process_group=process_group)
     S = pool_fuse(final_view_descriptors, sr.bins, num_group, pool=pool, empty_fill=empty_fill, layout=layout)

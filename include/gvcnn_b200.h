@@ -179,6 +179,18 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
                         int B, int V, int64_t D, int G, int pool,
                         int g_layout, int dtype, void *stream);
 
+/* --- the whole forward in one call ----------------------------------------
+ * gvcnn_score_bin_fwd + gvcnn_pool_fuse_fwd (per-shape scores, the reference's
+ * own weights): what one train.py step does between the backbone and the
+ * classifier (train.py:270-288 + nets/model.py:154-157), as two launches chained
+ * with programmatic dependent launch.  x / flags / tie_mask may be null. */
+int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, const void *F,
+                              float *x, float *scores, int32_t *bins, int32_t *flags,
+                              void *S, uint8_t *tie_mask, int32_t *status,
+                              int B, int V, int C, int64_t D, int G, int pool, float empty_fill,
+                              int r_layout, int f_layout, int dtype, int edge_ulps, int clamp,
+                              void *stream);
+
 /* --- paper mode: score-derived, differentiable group weights ---------------
  * No counterpart in the reference (its weight is 1 + count and its score FC gets
  * no gradient: nets/model.py:28-41, train.py:127-128).

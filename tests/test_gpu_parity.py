@@ -681,3 +681,43 @@ def test_reference_style_host_arrays_for_scheme_and_weight(model, golden_dir):
     np.testing.assert_array_equal(model.group_fusion(desc, torch.tensor(w)).cpu().numpy(), S)   # CPU tensor
     with pytest.raises(RuntimeError):
         model.view_pooling([torch.tensor(F[v]) for v in range(F.shape[0])], scheme)      # descriptors must be CUDA
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("pool", ["max", "mean"])
+@pytest.mark.parametrize("B,V,D", [(700, 12, 2048), (301, 6, 4096), (5, 12, 1024), (149, 12, 6144), (1, 6, 2048)])
+def test_one_call_forward_equals_staged_path(model, c_oracle, B, V, D, pool, dtype):
+    """gvcnn_grouping_fusion_fwd (the one-call forward used by model.grouping_fusion and bench.py) under the
+    default kernels and under the generic ones: same scores, bins, descriptors, tie masks (hence gradients),
+    and both match the oracle."""
+    from gvcnn_tf_b200 import _cabi
+    G, Cr = 8, 1024
+    F, _, dS = make_inputs(B + V + D, B, V, D, G, ties=True)
+    R, W, b = score_inputs(B + 3, B, V, Cr, bias_range=0.4)
+    td = torch.float32
+    if dtype == "bf16":
+        F, dS, R, td = O.round_bf16(F), O.round_bf16(dS), O.round_bf16(R), torch.bfloat16
+    outs = []
+    for variant in (0, 1):                       # 0: ring / V-templated kernels; 1: generic one-tile-per-CTA kernels
+        x = dev(F, td).requires_grad_(True)
+        try:
+            assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
+            S, sr = model.grouping_fusion(dev(R, td), dev(W), dev(b), x, G, pool=pool)
+            S.backward(dev(dS, td))
+            torch.cuda.synchronize()
+        finally:
+            _cabi.lib().gvcnn_set_pool_variant(0)
+        outs.append((S.detach().float().cpu().numpy(), sr.x.cpu().numpy(), sr.scores.cpu().numpy(),
+                     sr.bins.cpu().numpy(), sr.flags.cpu().numpy(), x.grad.float().cpu().numpy()))
+    for a, c in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, c)
+    bins = outs[0][3]
+    xk = c_oracle.view_score_x_kernel_order(R, W, b, E=8 if dtype == "bf16" else 4)
+    np.testing.assert_array_equal(outs[0][1], xk)
+    np.testing.assert_array_equal(bins, O.bins_from_scores(c_oracle.score_f32(xk), G))
+    want = c_oracle.pool_fuse_fwd(F, bins, G, pool, 1.0)
+    wantg = c_oracle.pool_fuse_bwd(dS, F, bins, G, pool)
+    if dtype == "bf16":
+        want, wantg = O.round_bf16(want), O.round_bf16(wantg)
+    np.testing.assert_array_equal(outs[0][0], want)
+    np.testing.assert_array_equal(outs[0][5], wantg)
