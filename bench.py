@@ -344,6 +344,27 @@ def run_cuda_arm(args):
     t_pool_m = statistics.mean(e[1].elapsed_time(e[2]) for e in evb)
     t_bwd = statistics.mean(e[2].elapsed_time(e[3]) for e in evb)
 
+    # ---- the reference-literal mode (one scheme per batch, nets/model.py:146): x per (shape, view), deterministic
+    #      column sums, V scores/bins, pooling with the shared bin row.  Reported beside the per-shape headline.
+    xb = torch.empty((B, V), dtype=torch.float32, device=dev)
+    xsum = torch.empty((1, V), dtype=torch.float32, device=dev)
+    sc1 = torch.empty((1, V), dtype=torch.float32, device=dev)
+    bins1 = torch.empty((1, V), dtype=torch.int32, device=dev)
+    bias_lit = (torch.rand(V, generator=torch.Generator().manual_seed(9)) * 8 - 4).to(dev)   # spread the batch means
+
+    def step_literal(i):
+        Fd, Rd, _ = sets[i % NSETS]
+        C.check(L.gvcnn_view_score_fwd(p(Rd), p(Wd), p(bias_lit), p(xb), B, V, Cr, C.LAYOUT_BVD, C.F32, sp), "view_score_fwd")
+        C.check(L.gvcnn_batch_sum_x(p(xb), p(xsum), B, V, sp), "batch_sum_x")
+        C.check(L.gvcnn_score_bin(p(xsum), ctypes.c_float(float(B)), p(sc1), p(bins1), None, p(status), V, G, 0, 1, sp),
+                "score_bin")
+        C.check(L.gvcnn_pool_fuse_fwd(p(Fd), p(bins1), 0, None, 0, p(S), None, None, p(status), B, V, D, G, pool, fill,
+                                      C.LAYOUT_BVD, C.F32, sp), "pool_fuse_fwd")
+
+    for i in range(3):
+        step_literal(i)
+    ms_literal = timed(step_literal, K)
+
     # ---- end to end through the host-buffer C-ABI entry point (pinned host memory)
     Ke = max(1, min(K, args.e2e_steps))
     Fh, Rh, dSh = (t.pin_memory() for t in host)
@@ -437,6 +458,9 @@ def run_cuda_arm(args):
                                                          if world > 1 else "no collective at N=1"),
                     "value": world * B * K / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / K,
                     "algorithmic_GBps_per_gpu": ach_train_step, "frac_of_peak": ach_train_step / peak},
+        "literal_batch_mode": {"workload": "same batch, reference-literal score_reduce='batch' (one scheme per batch, "
+                                           "nets/model.py:146): 4 launches", "value": world * B * K / (ms_literal * 1e-3),
+                               "unit": UNIT, "ms_per_step": ms_literal / K},
         "e2e": {"value": world * B * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
                 "api": "gvcnn_grouping_fusion_host (C ABI, pinned host buffers, chunk=%d shapes, 3-deep pipeline)" % chunk},
