@@ -19,6 +19,7 @@ STATUS_WORDS = 4
 STATUS_BIN_RANGE, STATUS_NAN, STATUS_NEAR_EDGE, STATUS_BAD_SCHEME = 0, 1, 2, 3
 FLAG_NEAR_EDGE, FLAG_BIN_RANGE, FLAG_NAN = 1, 2, 4
 MAX_VIEWS, MAX_GROUPS = 128, 4096
+E_UNSUPPORTED = -10
 
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 
@@ -42,6 +43,9 @@ SIGNATURES = {
                                  _i, _i, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_grouping_fusion_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "gvcnn_pool_fuse_gap_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "gvcnn_pool_fuse_gap_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "gvcnn_pool_fuse_gap_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_group_weight_from_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gvcnn_pool_fuse_bwd_weights": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_score_weight_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

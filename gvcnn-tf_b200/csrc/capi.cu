@@ -85,6 +85,7 @@ const char *gvcnn_strerror(int code)
     case GVCNN_E_NO_DEVICE: return "no CUDA device of compute capability 10.x (sm_100a only; no CPU fallback)";
     case GVCNN_E_BAD_MODE: return "unsupported pool / mode value";
     case GVCNN_E_WORKSPACE: return "workspace too small";
+    case GVCNN_E_UNSUPPORTED: return "shapes not supported by this specialised entry point (use the general one)";
     default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -280,6 +281,61 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
     if (rc) return rc;
     return gvcnn_pool_fuse_fwd(F, bins, V, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
                                f_layout, dtype, stream);
+}
+
+// ---------------------------------------------------------------------------
+// pooling + fusion with the following global average pooling folded in
+// ---------------------------------------------------------------------------
+size_t gvcnn_pool_fuse_gap_workspace_bytes(int B, int C, int HW, int dtype)
+{
+    if (B <= 0 || C <= 0 || HW <= 0) return 0;
+    return gap_workspace_bytes(B, C, HW, dtype);
+}
+
+int gvcnn_pool_fuse_gap_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b, void *S_gap, uint8_t *tie_mask,
+                            int32_t *status, void *workspace, size_t workspace_bytes, int B, int V, int HW, int C,
+                            int G, int pool, float empty_fill, int f_layout, int dtype, void *stream)
+{
+    if (HW <= 0 || C <= 0) return GVCNN_E_BAD_ARG;
+    const int64_t D = (int64_t)HW * C;
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
+    if (!bins || !S_gap || !workspace || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
+    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    ViewPtrs fp;
+    int64_t sb;
+    bool al;
+    rc = make_view_ptrs(F, f_layout, dtype, B, V, D, fp, sb, al);
+    if (rc) return rc;
+    const size_t need = gap_workspace_bytes(B, C, HW, dtype);
+    if (!al || need == 0 || V > 32 || (tie_mask && !is_aligned(tie_mask, 8)) || !is_aligned(workspace, 16))
+        return GVCNN_E_UNSUPPORTED;
+    if (workspace_bytes < need) return GVCNN_E_WORKSPACE;
+    rc = launch_pool_fuse_gap_fwd(fp, sb, bins, bin_stride_b, S_gap, tie_mask, status, static_cast<float *>(workspace),
+                                  B, V, HW, C, G, pool, empty_fill, dtype, static_cast<cudaStream_t>(stream));
+    return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
+}
+
+int gvcnn_pool_fuse_gap_bwd(const void *dS_gap, const int32_t *bins, int64_t bin_stride_b, const uint8_t *tie_mask,
+                            void *dF, int32_t *status, int B, int V, int HW, int C, int G, int pool, int g_layout,
+                            int dtype, void *stream)
+{
+    if (HW <= 0 || C <= 0) return GVCNN_E_BAD_ARG;
+    const int64_t D = (int64_t)HW * C;
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
+    if (!dS_gap || !bins || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
+    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    if (pool == GVCNN_POOL_MAX && !tie_mask) return GVCNN_E_BAD_ARG;
+    ViewPtrs gp;
+    int64_t sb;
+    bool al;
+    rc = make_view_ptrs(dF, g_layout, dtype, B, V, D, gp, sb, al);
+    if (rc) return rc;
+    if (!al || !is_aligned(dS_gap, 16) || (tie_mask && !is_aligned(tie_mask, 8))) return GVCNN_E_UNSUPPORTED;
+    rc = launch_pool_fuse_gap_bwd(dS_gap, bins, bin_stride_b, tie_mask, gp, sb, status, B, V, HW, C, G, pool, dtype,
+                                  static_cast<cudaStream_t>(stream));
+    return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
 }
 
 // ---------------------------------------------------------------------------

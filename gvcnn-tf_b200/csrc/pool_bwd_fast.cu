@@ -20,11 +20,14 @@ struct __align__(16) BwdPlan {
     uint32_t first_mask;            // bit k: sorted view k starts a group
 };
 
-template <typename T, int POOL, int V, int NT>
+// GAP: dS is the gradient of the global average pool that follows the fusion, [B, C] (D = HW * C,
+// channel-last): dS[b, p, c] = dOut[b, c] / HW (tf.reduce_mean's gradient), never materialised.
+template <typename T, int POOL, int V, int NT, bool GAP>
 __global__ void __launch_bounds__(NT)
 pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins, const int64_t bin_sb,
                           const uint8_t *__restrict__ mask, const ViewPtrs gp, const int64_t g_sb, int32_t *status,
-                          const int B, const int64_t D, const int G, const int tiles_per_shape)
+                          const int B, const int64_t D, const int G, const int tiles_per_shape, const int C,
+                          const int HW)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
@@ -46,7 +49,8 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
     uint32_t pwd[P][NW];
     if (active) {
-        raw = ldg_stream_16(dS + off);
+        if constexpr (GAP) raw = *reinterpret_cast<const uint4 *>(dS + (int64_t)b * C + (int)((d0 + e0) % C));
+        else raw = ldg_stream_16(dS + off);
         if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -102,6 +106,10 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
     const float rcp_sumw = __frcp_rn(sumw);
     float t[E];
     Elem<T>::unpack(raw, t);
+    if constexpr (GAP) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = __fdiv_rn(t[e], (float)HW);  // gradient of the mean over positions
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) t[e] = div_by_rcp(t[e], sumw, rcp_sumw);  // g0 = dS / sum_w
 
@@ -190,7 +198,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
 template <typename T, int V>
 static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int64_t D, int G, int pool,
-                             cudaStream_t st)
+                             cudaStream_t st, int gapC = 0, int gapHW = 0)
 {
     constexpr int NT = 256;
     constexpr int E = Elem<T>::kVec;
@@ -199,12 +207,15 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
     if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
     const unsigned grid = (unsigned)(B * tiles);
     cudaError_t err;
-    if (pool == GVCNN_POOL_MAX)
-        err = launch_pdl(pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MAX, V, NT>, dim3(grid), dim3(NT), 0, st,
-                         static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
-    else
-        err = launch_pdl(pool_fuse_bwd_fast_kernel<T, GVCNN_POOL_MEAN, V, NT>, dim3(grid), dim3(NT), 0, st,
-                         static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles);
+#define GVCNN_LAUNCH_BF(POOL_, GAP_)                                                                          \
+    err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_>, dim3(grid), dim3(NT), 0, st,           \
+                     static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles, gapC, gapHW)
+    if (gapC > 0) {
+        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, true);
+    } else {
+        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, false); else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, false);
+    }
+#undef GVCNN_LAUNCH_BF
     if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
@@ -224,6 +235,26 @@ static int launch_bwd_fast_t(const void *dS, const int32_t *bins, int64_t bin_sb
     case 20: return launch_bwd_fast_v<T, 20>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
     default: return -1000;
     }
+}
+
+// GAP-folded backward: dOut [B, C] -> dF; same applicability as the forward GAP kernel plus the fast-kernel V set
+int launch_pool_fuse_gap_bwd(const void *dOut, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
+                             const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int HW, int C, int G,
+                             int pool, int dtype, cudaStream_t st)
+{
+    const int64_t D = (int64_t)HW * C;
+    const int td = 256 * (dtype == GVCNN_F32 ? 4 : 8);
+    if (C % td != 0) return -1000;
+#define GVCNN_GAPB_CASE(T_)                                                                                   \
+    switch (V) {                                                                                              \
+    case 6: return launch_bwd_fast_v<T_, 6>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
+    case 8: return launch_bwd_fast_v<T_, 8>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
+    case 12: return launch_bwd_fast_v<T_, 12>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW); \
+    default: return -1000;                                                                                    \
+    }
+    if (dtype == GVCNN_F32) { GVCNN_GAPB_CASE(float) }
+    GVCNN_GAPB_CASE(__nv_bfloat16)
+#undef GVCNN_GAPB_CASE
 }
 
 // returns -1000 when this fast path does not apply

@@ -29,7 +29,7 @@ from . import _cabi as C
 __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion", "view_scores",
     "score_bin", "pool_fuse", "grouping_fusion", "GroupDescriptors", "ScoreResult",
-    "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status", "grouping_fusion_paper",
+    "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status", "grouping_fusion_paper", "pool_fuse_gap",
 ]
 
 _POOL = {"max": C.POOL_MAX, "mean": C.POOL_MEAN}
@@ -434,6 +434,85 @@ def pool_fuse(final_view_descriptors, bins, num_group, pool="max", empty_fill=1.
     return S
 
 
+class _PoolFuseGapFn(torch.autograd.Function):
+    """Pooling + fusion + the global average pooling that follows it (nets/model.py:154-163) without ever
+    writing the fused map: [B, C] out; backward takes the [B, C] gradient."""
+
+    @staticmethod
+    def forward(ctx, bins, G, pool, empty_fill, layout, HW, Cch, n_views, *views):
+        L = C.lib()
+        is_list = layout == "list"
+        fv = _Views(list(views) if is_list else views[0], None if is_list else layout, "F")
+        dev = fv.device
+        dt = _dtype_code(fv.dtype)
+        bins_c = bins.to(torch.int32).contiguous()
+        if bins_c.dim() == 1:
+            bins_c = bins_c[None]
+        bstride = fv.V if (bins_c.shape[0] == fv.B and fv.B > 1) else 0
+        need_grad = any(v.requires_grad for v in views)
+        out = torch.empty((fv.B, Cch), dtype=fv.dtype, device=dev)
+        mask = None
+        if need_grad and pool == "max":
+            mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
+        status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+        ws_bytes = L.gvcnn_pool_fuse_gap_workspace_bytes(fv.B, Cch, HW, dt)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            C.check(L.gvcnn_pool_fuse_gap_fwd(fv.arg, _ptr(bins_c), bstride, _ptr(out), _ptr(mask), _ptr(status),
+                                              _ptr(ws), ws_bytes, fv.B, fv.V, HW, Cch, G, _POOL[pool],
+                                              ctypes.c_float(empty_fill), fv.layout, dt, _stream()),
+                    "gvcnn_pool_fuse_gap_fwd")
+        ctx.fv, ctx.G, ctx.pool, ctx.HW, ctx.Cch, ctx.bstride = fv, G, pool, HW, Cch, bstride
+        ctx.save_for_backward(bins_c, mask if mask is not None else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(status)
+        return out, status
+
+    @staticmethod
+    def backward(ctx, dOut, _dstatus):
+        bins_c, mask = ctx.saved_tensors
+        mask = mask if mask.numel() else None
+        fv = ctx.fv
+        dOut = dOut.contiguous()
+        out, gv = fv.empty_like()
+        status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dOut.device)
+        with torch.cuda.device(dOut.device):
+            C.check(C.lib().gvcnn_pool_fuse_gap_bwd(_ptr(dOut), _ptr(bins_c), ctx.bstride, _ptr(mask), gv.arg,
+                                                    _ptr(status), gv.B, gv.V, ctx.HW, ctx.Cch, ctx.G, _POOL[ctx.pool],
+                                                    gv.layout, _dtype_code(gv.dtype), _stream()),
+                    "gvcnn_pool_fuse_gap_bwd")
+        grads = tuple(out) if isinstance(out, list) else (out,)
+        return (None,) * 8 + grads
+
+
+def pool_fuse_gap(final_view_descriptors, bins, num_group, pool="max", empty_fill=1.0, layout=None):
+    """view_pooling + group_fusion + GlobalAveragePooling2D (nets/model.py:154-163) in one pass: the
+    descriptors are channel-last maps ([N, h, w, C] per view, or [B, V, h, w, C] / [V, B, h, w, C]); returns
+    the pooled shape descriptor [N, C].  The fused map is never written.  Shapes the specialised kernel does
+    not cover (see gvcnn_pool_fuse_gap_fwd) run pool_fuse and average afterwards - same result up to the
+    float32 rounding of the mean."""
+    if isinstance(final_view_descriptors, (list, tuple)):
+        views, lay = tuple(final_view_descriptors), "list"
+        shp = tuple(views[0].shape)
+        spatial = shp[1:-1]
+    else:
+        views, lay = (final_view_descriptors,), (layout or "bvd")
+        shp = tuple(final_view_descriptors.shape)
+        spatial = shp[2:-1]
+    if len(shp) < 3:
+        raise ValueError("pool_fuse_gap expects channel-last maps, e.g. [N, h, w, C] per view")
+    Cch = shp[-1]
+    HW = int(math.prod(spatial)) if len(spatial) else 1
+    _require_cuda(bins, "bins")
+    try:
+        out, _ = _PoolFuseGapFn.apply(bins, num_group, pool, empty_fill, lay, HW, Cch, len(views), *views)
+        return out
+    except C.GvcnnError as e:
+        if e.code != C.E_UNSUPPORTED:
+            raise
+    S = pool_fuse(final_view_descriptors, bins, num_group, pool=pool, empty_fill=empty_fill, layout=layout)
+    return S.reshape(S.shape[0], -1, Cch).mean(dim=1)
+
+
 class GroupDescriptors(dict):
     """What ``view_pooling`` returns: behaves like the reference's
     ``{group index: pooled descriptor}`` dict (nets/model.py:61,72), but lazy -
@@ -721,11 +800,19 @@ class GVCNNHead(torch.nn.Module):
         torch.nn.init.uniform_(self.classifier.weight, -lim2, lim2)
         torch.nn.init.zeros_(self.classifier.bias)
 
-    def forward(self, raw_view_descriptors, final_view_descriptors, process_group=None, check=True):
+    def forward(self, raw_view_descriptors, final_view_descriptors, process_group=None, check=True, fold_gap=False):
         """raw: post-GAP block3 features [N, V, C_raw] (or list of V [N, C_raw]);
         final: list of V [N, h, w, C] maps or [N, V, h, w, C].  Returns
         (view_discrimination_scores, shape_descriptor, logits) like
-        nets/model.py:166."""
+        nets/model.py:166.  fold_gap=True (reference-literal weights only) folds the
+        GlobalAveragePooling2D of nets/model.py:163 into the pooling kernel: the fused
+        map is never written and the second return value is the pooled [N, C] descriptor."""
+        if fold_gap and self.weight_mode == "count":
+            sr = score_bin(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
+                           self.num_group, score_reduce=self.score_reduce, process_group=process_group, check=check)
+            net = pool_fuse_gap(final_view_descriptors, sr.bins, self.num_group, pool=self.pool,
+                                empty_fill=self.empty_fill)
+            return sr.scores, net, self.classifier(net.to(self.classifier.weight.dtype))
         if self.weight_mode == "score":
             S, scores, _, _ = grouping_fusion_paper(raw_view_descriptors, self.score_kernel, self.score_bias,
                                                     final_view_descriptors, self.num_group, pool=self.pool)

@@ -77,6 +77,7 @@ extern "C" {
 #define GVCNN_E_NO_DEVICE (-7)   /* no CUDA device / not compute capability 10.x */
 #define GVCNN_E_BAD_MODE (-8)
 #define GVCNN_E_WORKSPACE (-9)   /* workspace too small                          */
+#define GVCNN_E_UNSUPPORTED (-10) /* specialised entry point: shapes not covered */
 
 int gvcnn_version(void);
 const char *gvcnn_strerror(int code);
@@ -190,6 +191,31 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
                               int B, int V, int C, int64_t D, int G, int pool, float empty_fill,
                               int r_layout, int f_layout, int dtype, int edge_ulps, int clamp,
                               void *stream);
+
+/* --- pooling + fusion with the following global average pooling folded in ---
+ * nets/model.py:154-163: view_pooling -> group_fusion -> GlobalAveragePooling2D.
+ * The descriptors are channel-last maps, D = HW * C per view (nets/model.py:149:
+ * [N, 10, 10, 2048]); S_gap [B, C] (in `dtype`) = mean over the HW positions of
+ * the fused map, which is never written to memory (saves D*s bytes per shape in
+ * the forward and the read of dS in the backward).  Per-position arithmetic is
+ * exactly gvcnn_pool_fuse_fwd's; positions are added in order (split into a few
+ * ascending chunks for parallelism, see gvcnn_pool_fuse_gap_workspace_bytes),
+ * then divided by HW.  Supported: 16-byte aligned rows, V in {6, 8, 12},
+ * C a multiple of 1024 (f32) / 2048 (bf16), G <= 255, the reference's own
+ * weights; anything else returns GVCNN_E_UNSUPPORTED (use gvcnn_pool_fuse_fwd
+ * and pool afterwards).  tie_mask as in gvcnn_pool_fuse_fwd ([ceil(V/8), B, D]).
+ * gvcnn_pool_fuse_gap_bwd: dS_gap [B, C] -> dF (dS[b,p,c] = dS_gap[b,c] / HW is
+ * never materialised). */
+size_t gvcnn_pool_fuse_gap_workspace_bytes(int B, int C, int HW, int dtype);
+int gvcnn_pool_fuse_gap_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b,
+                            void *S_gap, uint8_t *tie_mask, int32_t *status,
+                            void *workspace, size_t workspace_bytes,
+                            int B, int V, int HW, int C, int G, int pool, float empty_fill,
+                            int f_layout, int dtype, void *stream);
+int gvcnn_pool_fuse_gap_bwd(const void *dS_gap, const int32_t *bins, int64_t bin_stride_b,
+                            const uint8_t *tie_mask, void *dF, int32_t *status,
+                            int B, int V, int HW, int C, int G, int pool,
+                            int g_layout, int dtype, void *stream);
 
 /* --- paper mode: score-derived, differentiable group weights ---------------
  * No counterpart in the reference (its weight is 1 + count and its score FC gets

@@ -35,6 +35,11 @@ for B, V, D, G, dt, pool in cases:
     _ = model.group_fusion(desc, torch.rand(G, device=dev) + 0.5)
     sb = model.score_bin(R, W, b + 1.0, G, score_reduce="batch")
     torch.cuda.synchronize()
+# GAP-folded pooling (real geometry, small)
+Fm = [torch.relu(torch.randn(3, 5, 5, 2048, device=dev)).requires_grad_(True) for _ in range(6)]
+out = model.pool_fuse_gap(Fm, torch.randint(0, 10, (3, 6), dtype=torch.int32, device=dev), 10)
+out.sum().backward()
+torch.cuda.synchronize()
 # paper mode
 F = torch.relu(torch.randn(6, 12, 512, device=dev)).requires_grad_(True)
 R = torch.randn(6, 12, 256, device=dev).requires_grad_(True)

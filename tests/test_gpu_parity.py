@@ -721,3 +721,56 @@ def test_one_call_forward_equals_staged_path(model, c_oracle, B, V, D, pool, dty
         want, wantg = O.round_bf16(want), O.round_bf16(wantg)
     np.testing.assert_array_equal(outs[0][0], want)
     np.testing.assert_array_equal(outs[0][5], wantg)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
+@pytest.mark.parametrize("N,V,h,w,Cc", [(4, 6, 10, 10, 2048), (37, 12, 3, 3, 2048), (300, 12, 1, 1, 2048), (2, 8, 5, 4, 4096)])
+def test_gap_folded_pooling(model, c_oracle, N, V, h, w, Cc, pool, fill, dtype):
+    """pooling + fusion + GlobalAveragePooling2D (nets/model.py:154-163) without writing the fused
+    map.  Forward = mean over positions of the oracle's S; backward = the oracle's dF for dS = dOut / (h*w).
+    The per-position arithmetic is bit-identical; the mean's summation order is ours, so 1e-5 relative
+    (north_star's float32 bar) / 1e-2 for bf16."""
+    G, HW = 8, h * w
+    rng = np.random.default_rng(N + V + HW)
+    F = np.maximum(rng.standard_normal((N, V, h, w, Cc)), -0.3).astype(np.float32)
+    bins = rng.integers(0, G, (N, V)).astype(np.int32)
+    dOut = rng.standard_normal((N, Cc)).astype(np.float32)
+    td, rtol = torch.float32, 1e-5
+    if dtype == "bf16":
+        F, dOut, td, rtol = O.round_bf16(F), O.round_bf16(dOut), torch.bfloat16, 1e-2
+    views = [dev(F[:, v], td).requires_grad_(True) for v in range(V)]          # the reference's list of maps
+    out = model.pool_fuse_gap(views, dev(bins), G, pool=pool, empty_fill=fill)
+    assert tuple(out.shape) == (N, Cc)
+    S = c_oracle.pool_fuse_fwd(F.reshape(N, V, -1), bins, G, pool, fill).reshape(N, HW, Cc)
+    want = S.astype(np.float64).mean(axis=1)
+    np.testing.assert_allclose(out.detach().float().cpu().numpy(), want, rtol=rtol, atol=rtol * np.abs(want).max())
+    out.backward(dev(dOut, td))
+    dS = np.repeat((dOut / np.float32(HW))[:, None, :], HW, axis=1).reshape(N, -1).astype(np.float32)
+    wantg = c_oracle.pool_fuse_bwd(dS, F.reshape(N, V, -1), bins, G, pool).reshape(N, V, h, w, Cc)
+    got = np.stack([v.grad.float().cpu().numpy() for v in views], axis=1)
+    if dtype == "bf16":
+        np.testing.assert_allclose(got, wantg, rtol=1e-2, atol=1e-2 * np.abs(wantg).max())
+    else:
+        np.testing.assert_array_equal(got, wantg)                               # gradient path is exact
+    # unsupported shapes (C not a multiple of the tile) fall back to pool_fuse + mean: same numbers
+    if dtype == "fp32" and N <= 4:
+        F2 = F[..., :96].copy()
+        out2 = model.pool_fuse_gap(dev(F2), dev(bins), G, pool=pool, empty_fill=fill)
+        S2 = c_oracle.pool_fuse_fwd(F2.reshape(N, V, -1), bins, G, pool, fill).reshape(N, HW, 96)
+        np.testing.assert_allclose(out2.cpu().numpy(), S2.astype(np.float64).mean(axis=1), rtol=1e-5, atol=1e-6)
+
+
+def test_head_fold_gap(model):
+    torch.manual_seed(1)
+    N, V, Cr, Cf, G = 5, 6, 64, 2048, 10
+    head = model.GVCNNHead(V, Cr, Cf, 7, num_group=G).cuda()
+    with torch.no_grad():
+        head.score_bias.uniform_(-3, 3)
+    raw = torch.randn(N, V, Cr, device="cuda")
+    final = [torch.relu(torch.randn(N, 4, 4, Cf, device="cuda")) for _ in range(V)]
+    s1, S, logits1 = head(raw, final)
+    s2, net, logits2 = head(raw, final, fold_gap=True)
+    assert tuple(net.shape) == (N, Cf) and torch.equal(s1, s2)
+    torch.testing.assert_close(net, S.reshape(N, -1, Cf).mean(dim=1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits2, logits1, rtol=1e-4, atol=1e-5)
