@@ -9,6 +9,6 @@ Everything computes in ``libgvcnn_sm100.so`` (``csrc/``, C ABI in ``include/gvcn
 there is no CPU or pure-PyTorch fallback.
 """
 from . import _cabi, model  # noqa: F401
-from . import parallel  # noqa: F401
+from . import parallel, records  # noqa: F401
 
 __version__ = "0.1.0"
