@@ -212,9 +212,10 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
          (!group_desc || is_aligned(group_desc, 16));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
     const int variant = g_pool_variant.load();
-    if (al && !weights && !group_desc && (variant == 0 || variant == 3)) {
-        // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu)
-        rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool,
+    if (al && (!weights || empty_fill == 0.0f) && !group_desc && (variant == 0 || variant == 3)) {
+        // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu); with caller-supplied weights only
+        // when empty groups contribute nothing (empty_fill == 0, e.g. paper mode)
+        rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, weights, weight_stride_b, S, tie_mask, status, B, V, D, G, pool,
                                        empty_fill, dtype, static_cast<cudaStream_t>(stream));
         if (rc != -1000) return rc;
     }
@@ -241,9 +242,9 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     al = al && is_aligned(dS, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
     const int variant = g_pool_variant.load();
-    if (al && !weights && (variant == 0 || variant == 3)) {
+    if (al && (variant == 0 || variant == 3)) {
         // fast path: V-templated kernel (pool_bwd_fast.cu)
-        rc = launch_pool_fuse_bwd_fast(dS, bins, bin_stride_b, tie_mask, gp, sb, status, B, V, D, G, pool, dtype,
+        rc = launch_pool_fuse_bwd_fast(dS, bins, bin_stride_b, tie_mask, weights, weight_stride_b, gp, sb, status, B, V, D, G, pool, dtype,
                                        static_cast<cudaStream_t>(stream));
         if (rc != -1000) return rc;
     }
@@ -361,8 +362,9 @@ int gvcnn_pool_fuse_bwd_weights(const void *F, const void *dS, const void *S, co
     bool al;
     rc = make_view_ptrs(F, f_layout, dtype, B, V, D, fp, sb, al);
     if (rc) return rc;
+    al = al && is_aligned(dS, 16) && is_aligned(S, 16) && (D * elt_size(dtype)) % 16 == 0;
     return launch_group_weight_grad(fp, sb, dS, S, bins, bin_stride_b, weights, weight_stride_b, dweights, B, V, D, G,
-                                    pool, dtype, static_cast<cudaStream_t>(stream));
+                                    pool, dtype, al, static_cast<cudaStream_t>(stream));
 }
 
 int gvcnn_score_weight_bwd(const float *dweights, const int32_t *bins, const float *x, float *dx, int rows, int V,
@@ -388,14 +390,16 @@ int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *
     bool al;
     rc = make_view_ptrs(R, r_layout, dtype, B, V, C, rp, sb, al);
     if (rc) return rc;
+    bool al2 = true;
     if (dR) {
-        rc = make_view_ptrs(dR, r_layout, dtype, B, V, C, drp, dsb, al);
+        rc = make_view_ptrs(dR, r_layout, dtype, B, V, C, drp, dsb, al2);
         if (rc) return rc;
     } else {
         drp = rp;
     }
     return launch_view_score_bwd(rp, sb, dx, W, dW, dbias, drp, dsb, dR ? 1 : 0, static_cast<float *>(workspace),
-                                 GVCNN_SCORE_BWD_SLICES, B, V, C, dtype, static_cast<cudaStream_t>(stream));
+                                 GVCNN_SCORE_BWD_SLICES, B, V, C, dtype, al && al2,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------

@@ -321,14 +321,14 @@ int launch_group_weight_from_scores(const float *scores, const int32_t *bins, fl
                                     cudaStream_t st);
 int launch_group_weight_grad(const ViewPtrs &fp, int64_t f_sb, const void *dS, const void *S, const int32_t *bins,
                              int64_t bin_sb, const float *weights, int64_t w_sb, float *dweights, int B, int V,
-                             int64_t D, int G, int pool, int dtype, cudaStream_t st);
+                             int64_t D, int G, int pool, int dtype, bool aligned16, cudaStream_t st);
 int launch_score_weight_bwd(const float *dweights, const int32_t *bins, const float *x, float *dx, int rows, int V,
                             int G, cudaStream_t st);
 int launch_view_score_bwd(const ViewPtrs &rp, int64_t r_sb, const float *dx, const float *W, float *dW, float *dbias,
                           const ViewPtrs &drp, int64_t dr_sb, int want_dr, float *workspace, int NS, int B, int V,
-                          int C, int dtype, cudaStream_t st);
-int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
-                              uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
+                          int C, int dtype, bool aligned16, cudaStream_t st);
+int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb,
+                              const float *weights, int64_t w_sb, void *S, uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
                               float fill, int dtype, cudaStream_t st);
 size_t gap_workspace_bytes(int B, int C, int HW, int dtype);
 int launch_pool_fuse_gap_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *out,
@@ -338,7 +338,7 @@ int launch_pool_fuse_gap_bwd(const void *dOut, const int32_t *bins, int64_t bin_
                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int HW, int C, int G,
                              int pool, int dtype, cudaStream_t st);
 int launch_pool_fuse_bwd_fast(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
-                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                              const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
                               int pool, int dtype, cudaStream_t st);
 int launch_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
                          const float *weights, int64_t w_sb,

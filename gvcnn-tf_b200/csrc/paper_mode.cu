@@ -51,7 +51,8 @@ __device__ __forceinline__ float block_sum_256(float v, float *scratch /* [8] */
 
 // One CTA per shape.  For every non-empty group, one streaming pass over its members' rows:
 // A_g = <dS, P_g>; then C = <dS, S>;  dw_g = (A_g - C) / sum_w.  Every view row is read once in total.
-template <typename T, int POOL>
+// VEC: 16-byte loads (rows 16-byte aligned, D a multiple of the vector width).
+template <typename T, int POOL, bool VEC>
 __global__ void __launch_bounds__(256) group_weight_grad_kernel(const ViewPtrs fp, const int64_t f_sb,
                                                                const T *__restrict__ dS, const T *__restrict__ S,
                                                                const int32_t *__restrict__ bins, const int64_t bin_sb,
@@ -59,39 +60,53 @@ __global__ void __launch_bounds__(256) group_weight_grad_kernel(const ViewPtrs f
                                                                float *__restrict__ dweights, const int V,
                                                                const int64_t D, const int G)
 {
+    constexpr int E = VEC ? Elem<T>::kVec : 1;
     __shared__ Plan plan;
     __shared__ float scratch[8];
     const int b = blockIdx.x;
     build_plan(plan, bins + (int64_t)b * bin_sb, V, G, nullptr, weights + (int64_t)b * w_sb);
     const T *dsrow = dS + (int64_t)b * D;
     const T *srow = S + (int64_t)b * D;
+    auto load = [&](const T *ptr, float (&f)[E]) {
+        if constexpr (VEC) Elem<T>::unpack(*reinterpret_cast<const uint4 *>(ptr), f);
+        else f[0] = Elem<T>::to_float(*ptr);
+    };
     float c = 0.0f;
-    for (int64_t d = threadIdx.x; d < D; d += 256)
-        c = fmaf(Elem<T>::to_float(dsrow[d]), Elem<T>::to_float(srow[d]), c);
+    for (int64_t d = (int64_t)threadIdx.x * E; d < D; d += 256 * E) {
+        float g[E], sv[E];
+        load(dsrow + d, g);
+        load(srow + d, sv);
+#pragma unroll
+        for (int e = 0; e < E; ++e) c = fmaf(g[e], sv[e], c);
+    }
     const float C = block_sum_256(c, scratch);
     const float sumw = plan.sumw;
-    for (int g = threadIdx.x; g < G; g += 256) dweights[(int64_t)b * G + g] = 0.0f;  // empty groups: P = fill, but w = 0
+    for (int g = threadIdx.x; g < G; g += 256) dweights[(int64_t)b * G + g] = 0.0f;  // empty groups: w = 0 in paper mode
     __syncthreads();
     int k = 0;
     while (k < V) {
         const int len = plan.glen[k];
         const int g = plan.gbin[k];
         float a = 0.0f;
-        for (int64_t d = threadIdx.x; d < D; d += 256) {
-            float p = Elem<T>::to_float(reinterpret_cast<const T *>(fp.p[plan.order[k]])[(int64_t)b * f_sb + d]);
+        for (int64_t d = (int64_t)threadIdx.x * E; d < D; d += 256 * E) {
+            float p[E], x[E], gs[E];
+            load(reinterpret_cast<const T *>(fp.p[plan.order[k]]) + (int64_t)b * f_sb + d, p);
             for (int j = 1; j < len; ++j) {
-                const float x = Elem<T>::to_float(reinterpret_cast<const T *>(fp.p[plan.order[k + j]])[(int64_t)b * f_sb + d]);
-                p = (POOL == GVCNN_POOL_MAX) ? fmaxf(p, x) : __fadd_rn(p, x);
+                load(reinterpret_cast<const T *>(fp.p[plan.order[k + j]]) + (int64_t)b * f_sb + d, x);
+#pragma unroll
+                for (int e = 0; e < E; ++e) p[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(p[e], x[e]) : __fadd_rn(p[e], x[e]);
             }
-            if (POOL == GVCNN_POOL_MEAN) p = __fdiv_rn(p, (float)len);
-            a = fmaf(Elem<T>::to_float(dsrow[d]), p, a);
+            load(dsrow + d, gs);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (POOL == GVCNN_POOL_MEAN) p[e] = __fdiv_rn(p[e], (float)len);
+                a = fmaf(gs[e], p[e], a);
+            }
         }
         const float A = block_sum_256(a, scratch);
         if (threadIdx.x == 0) dweights[(int64_t)b * G + g] = __fdiv_rn(__fsub_rn(A, C), sumw);
         k += len;
     }
-    // empty groups with a non-zero fill would have dw = (fill * sum(dS) - C) / sum_w; paper mode uses w = 0
-    // for them and the shim passes empty_fill = 0, so their weight gradient is irrelevant (set to 0 above).
 }
 
 // dx[row, v] = dw[row, bin_v] / n_{bin_v} * sign(x) / (1 + |x|)^2     (s = |x| / (1 + |x|))
@@ -114,8 +129,9 @@ __global__ void __launch_bounds__(256) score_weight_bwd_kernel(const float *__re
 }
 
 // partial[slice, v, c] = sum_{b in slice, ascending} dx[b, v] * R[b, v, c];  pbias[slice, v] = sum dx[b, v];
-// optionally dR[b, v, c] = dx[b, v] * W[v, c].  grid = (V, NS); 256 threads stride over C.
-template <typename T>
+// optionally dR[b, v, c] = dx[b, v] * W[v, c].  grid = (V, NS); a thread owns E consecutive channels
+// (16-byte loads when VEC) and walks its slice of the batch 4 shapes at a time (loads in flight).
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) view_score_bwd_partial_kernel(const ViewPtrs rp, const int64_t r_sb,
                                                                     const float *__restrict__ dx,
                                                                     const float *__restrict__ W,
@@ -124,17 +140,43 @@ __global__ void __launch_bounds__(256) view_score_bwd_partial_kernel(const ViewP
                                                                     const int64_t dr_sb, const int want_dr,
                                                                     const int B, const int V, const int C, const int NS)
 {
+    constexpr int E = VEC ? Elem<T>::kVec : 1;
+    constexpr int U = 4;
     const int v = blockIdx.x, sl = blockIdx.y;
     const int b0 = (int)((int64_t)B * sl / NS), b1 = (int)((int64_t)B * (sl + 1) / NS);
-    for (int c = threadIdx.x; c < C; c += 256) {
-        float acc = 0.0f;
-        const float wv = W[(int64_t)v * C + c];
-        for (int b = b0; b < b1; ++b) {
-            const float g = dx[(int64_t)b * V + v];
-            acc = fmaf(g, Elem<T>::to_float(reinterpret_cast<const T *>(rp.p[v])[(int64_t)b * r_sb + c]), acc);
-            if (want_dr) reinterpret_cast<T *>(drp.p[v])[(int64_t)b * dr_sb + c] = Elem<T>::from_float(__fmul_rn(g, wv));
+    const T *rbase = reinterpret_cast<const T *>(rp.p[v]);
+    T *drbase = reinterpret_cast<T *>(drp.p[v]);
+    for (int c = threadIdx.x * E; c < C; c += 256 * E) {
+        float acc[E], wv[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { acc[e] = 0.0f; wv[e] = W[(int64_t)v * C + c + e]; }
+        for (int b = b0; b < b1; b += U) {
+            float r[U][E], g[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int bb = min(b + u, b1 - 1);
+                g[u] = (b + u < b1) ? dx[(int64_t)bb * V + v] : 0.0f;
+                if constexpr (VEC) Elem<T>::unpack(ldg_stream_16(rbase + (int64_t)bb * r_sb + c), r[u]);
+                else r[u][0] = Elem<T>::to_float(rbase[(int64_t)bb * r_sb + c]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (b + u < b1) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(g[u], r[u][e], acc[e]);
+                    if (want_dr) {
+                        float o[E];
+#pragma unroll
+                        for (int e = 0; e < E; ++e) o[e] = __fmul_rn(g[u], wv[e]);
+                        T *dst = drbase + (int64_t)(b + u) * dr_sb + c;
+                        if constexpr (VEC) stg_stream_16(dst, Elem<T>::pack(o));
+                        else *dst = Elem<T>::from_float(o[0]);
+                    }
+                }
+            }
         }
-        partial[((int64_t)sl * V + v) * C + c] = acc;
+#pragma unroll
+        for (int e = 0; e < E; ++e) partial[((int64_t)sl * V + v) * C + c + e] = acc[e];
     }
     if (threadIdx.x == 0) {
         float s = 0.0f;
@@ -172,12 +214,19 @@ int launch_group_weight_from_scores(const float *scores, const int32_t *bins, fl
 
 int launch_group_weight_grad(const ViewPtrs &fp, int64_t f_sb, const void *dS, const void *S, const int32_t *bins,
                              int64_t bin_sb, const float *weights, int64_t w_sb, float *dweights, int B, int V,
-                             int64_t D, int G, int pool, int dtype, cudaStream_t st)
+                             int64_t D, int G, int pool, int dtype, bool aligned16, cudaStream_t st)
 {
 #define GVCNN_LAUNCH_GWG(T_, POOL_)                                                                              \
-    group_weight_grad_kernel<T_, POOL_><<<B, 256, 0, st>>>(fp, f_sb, static_cast<const T_ *>(dS),               \
-                                                           static_cast<const T_ *>(S), bins, bin_sb, weights,   \
-                                                           w_sb, dweights, V, D, G)
+    do {                                                                                                         \
+        if (aligned16 && D % Elem<T_>::kVec == 0)                                                                \
+            group_weight_grad_kernel<T_, POOL_, true><<<B, 256, 0, st>>>(                                        \
+                fp, f_sb, static_cast<const T_ *>(dS), static_cast<const T_ *>(S), bins, bin_sb, weights, w_sb,  \
+                dweights, V, D, G);                                                                              \
+        else                                                                                                     \
+            group_weight_grad_kernel<T_, POOL_, false><<<B, 256, 0, st>>>(                                       \
+                fp, f_sb, static_cast<const T_ *>(dS), static_cast<const T_ *>(S), bins, bin_sb, weights, w_sb,  \
+                dweights, V, D, G);                                                                              \
+    } while (0)
     if (dtype == GVCNN_F32) {
         if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_GWG(float, GVCNN_POOL_MAX); else GVCNN_LAUNCH_GWG(float, GVCNN_POOL_MEAN);
     } else {
@@ -197,17 +246,22 @@ int launch_score_weight_bwd(const float *dweights, const int32_t *bins, const fl
 
 int launch_view_score_bwd(const ViewPtrs &rp, int64_t r_sb, const float *dx, const float *W, float *dW, float *dbias,
                           const ViewPtrs &drp, int64_t dr_sb, int want_dr, float *workspace, int NS, int B, int V,
-                          int C, int dtype, cudaStream_t st)
+                          int C, int dtype, bool aligned16, cudaStream_t st)
 {
     float *partial = workspace;
     float *pbias = workspace + (size_t)NS * V * C;
     const dim3 grid(V, NS);
-    if (dtype == GVCNN_F32)
-        view_score_bwd_partial_kernel<float><<<grid, 256, 0, st>>>(rp, r_sb, dx, W, partial, pbias, drp, dr_sb, want_dr,
-                                                                  B, V, C, NS);
-    else
-        view_score_bwd_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(rp, r_sb, dx, W, partial, pbias, drp, dr_sb,
-                                                                          want_dr, B, V, C, NS);
+#define GVCNN_LAUNCH_VSB(T_)                                                                                   \
+    do {                                                                                                       \
+        if (aligned16 && C % Elem<T_>::kVec == 0)                                                              \
+            view_score_bwd_partial_kernel<T_, true><<<grid, 256, 0, st>>>(rp, r_sb, dx, W, partial, pbias, drp, \
+                                                                         dr_sb, want_dr, B, V, C, NS);         \
+        else                                                                                                   \
+            view_score_bwd_partial_kernel<T_, false><<<grid, 256, 0, st>>>(rp, r_sb, dx, W, partial, pbias, drp, \
+                                                                          dr_sb, want_dr, B, V, C, NS);        \
+    } while (0)
+    if (dtype == GVCNN_F32) GVCNN_LAUNCH_VSB(float); else GVCNN_LAUNCH_VSB(__nv_bfloat16);
+#undef GVCNN_LAUNCH_VSB
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
     const int64_t n = (int64_t)V * C;

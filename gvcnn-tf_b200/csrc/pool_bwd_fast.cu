@@ -17,6 +17,8 @@ namespace gvcnn {
 struct __align__(16) BwdPlan {
     unsigned long long rowptr[32];  // k -> byte address of row (b, view order[k]) at this tile's d0
     uint32_t seg[32];               // at a group start k: bitmask of the group's sorted positions
+    float gw[32];                   // caller-supplied weights only: weight of the group of sorted view k
+    float sumw;                     // caller-supplied weights only: sum of all G weights (left to right)
     uint32_t first_mask;            // bit k: sorted view k starts a group
 };
 
@@ -25,7 +27,8 @@ struct __align__(16) BwdPlan {
 template <typename T, int POOL, int V, int NT, bool GAP>
 __global__ void __launch_bounds__(NT)
 pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins, const int64_t bin_sb,
-                          const uint8_t *__restrict__ mask, const ViewPtrs gp, const int64_t g_sb, int32_t *status,
+                          const uint8_t *__restrict__ mask, const float *__restrict__ weights, const int64_t w_sb,
+                          const ViewPtrs gp, const int64_t g_sb, int32_t *status,
                           const int B, const int64_t D, const int G, const int tiles_per_shape, const int C,
                           const int HW)
 {
@@ -96,14 +99,23 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             const int start = k - same_before;
             plan.seg[k] = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << start;
             plan.rowptr[k] = (unsigned long long)(gp.p[lane] + ((int64_t)b * g_sb + d0) * (int64_t)sizeof(T));
+            if (weights) plan.gw[k] = __ldg(weights + (int64_t)b * w_sb + bin);
         }
-        if (lane == 0) plan.first_mask = fm;
+        if (lane == 0) {
+            plan.first_mask = fm;
+            if (weights) {
+                float sw = 0.0f;
+                for (int g = 0; g < G; ++g) sw = __fadd_rn(sw, __ldg(weights + (int64_t)b * w_sb + g));
+                plan.sumw = sw;
+            }
+        }
     }
     __syncthreads();
     if (!active) return;
 
-    const float sumw = (float)(G + V);
-    const float rcp_sumw = __frcp_rn(sumw);
+    const bool wts = weights != nullptr;
+    const float sumw = wts ? plan.sumw : (float)(G + V);
+    const float rcp_sumw = __frcp_rn((float)(G + V));
     float t[E];
     Elem<T>::unpack(raw, t);
     if constexpr (GAP) {
@@ -111,7 +123,8 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
         for (int e = 0; e < E; ++e) t[e] = __fdiv_rn(t[e], (float)HW);  // gradient of the mean over positions
     }
 #pragma unroll
-    for (int e = 0; e < E; ++e) t[e] = div_by_rcp(t[e], sumw, rcp_sumw);  // g0 = dS / sum_w
+    for (int e = 0; e < E; ++e)  // g0 = dS / sum_w
+        t[e] = wts ? __fdiv_rn(t[e], sumw) : div_by_rcp(t[e], sumw, rcp_sumw);
 
     const uint32_t fm = plan.first_mask;
     const uint32_t thread_off = (uint32_t)e0 * (uint32_t)sizeof(T);
@@ -132,7 +145,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
         for (int k = 0; k < V; ++k) {
             if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
                 const uint32_t seg = plan.seg[k];
-                const float w = (float)(1 + __popc(seg));
+                const float w = wts ? plan.gw[k] : (float)(1 + __popc(seg));
                 float val[E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
@@ -171,7 +184,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
                 const uint32_t seg = plan.seg[k];
                 const int n = __popc(seg);
-                const float w = (float)(1 + n);
+                const float w = wts ? plan.gw[k] : (float)(1 + n);
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const float g1 = __fmul_rn(t[e], w);
@@ -197,7 +210,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
 
 template <typename T, int V>
 static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
-                             const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int64_t D, int G, int pool,
+                             const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int64_t D, int G, int pool,
                              cudaStream_t st, int gapC = 0, int gapHW = 0)
 {
     constexpr int NT = 256;
@@ -209,7 +222,8 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
     cudaError_t err;
 #define GVCNN_LAUNCH_BF(POOL_, GAP_)                                                                          \
     err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_>, dim3(grid), dim3(NT), 0, st,           \
-                     static_cast<const T *>(dS), bins, bin_sb, mask, gp, g_sb, status, B, D, G, (int)tiles, gapC, gapHW)
+                     static_cast<const T *>(dS), bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G,   \
+                     (int)tiles, gapC, gapHW)
     if (gapC > 0) {
         if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, true);
     } else {
@@ -222,17 +236,17 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
 
 template <typename T>
 static int launch_bwd_fast_t(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
-                             const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                             const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
                              int pool, cudaStream_t st)
 {
     if (D < 256 * Elem<T>::kVec) return -1000;
     switch (V) {
-    case 4: return launch_bwd_fast_v<T, 4>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
-    case 6: return launch_bwd_fast_v<T, 6>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
-    case 8: return launch_bwd_fast_v<T, 8>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
-    case 12: return launch_bwd_fast_v<T, 12>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
-    case 16: return launch_bwd_fast_v<T, 16>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
-    case 20: return launch_bwd_fast_v<T, 20>(dS, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st);
+    case 4: return launch_bwd_fast_v<T, 4>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+    case 6: return launch_bwd_fast_v<T, 6>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+    case 8: return launch_bwd_fast_v<T, 8>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+    case 12: return launch_bwd_fast_v<T, 12>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+    case 16: return launch_bwd_fast_v<T, 16>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+    case 20: return launch_bwd_fast_v<T, 20>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
     default: return -1000;
     }
 }
@@ -247,9 +261,9 @@ int launch_pool_fuse_gap_bwd(const void *dOut, const int32_t *bins, int64_t bin_
     if (C % td != 0) return -1000;
 #define GVCNN_GAPB_CASE(T_)                                                                                   \
     switch (V) {                                                                                              \
-    case 6: return launch_bwd_fast_v<T_, 6>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
-    case 8: return launch_bwd_fast_v<T_, 8>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
-    case 12: return launch_bwd_fast_v<T_, 12>(dOut, bins, bin_sb, mask, gp, g_sb, status, B, D, G, pool, st, C, HW); \
+    case 6: return launch_bwd_fast_v<T_, 6>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
+    case 8: return launch_bwd_fast_v<T_, 8>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
+    case 12: return launch_bwd_fast_v<T_, 12>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW); \
     default: return -1000;                                                                                    \
     }
     if (dtype == GVCNN_F32) { GVCNN_GAPB_CASE(float) }
@@ -259,15 +273,15 @@ int launch_pool_fuse_gap_bwd(const void *dOut, const int32_t *bins, int64_t bin_
 
 // returns -1000 when this fast path does not apply
 int launch_pool_fuse_bwd_fast(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
-                              const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
+                              const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
                               int pool, int dtype, cudaStream_t st)
 {
     if (dtype == GVCNN_F32) {
         if (D % 4) return -1000;
-        return launch_bwd_fast_t<float>(dS, bins, bin_sb, mask, gp, g_sb, status, B, V, D, G, pool, st);
+        return launch_bwd_fast_t<float>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, V, D, G, pool, st);
     }
     if (D % 8) return -1000;
-    return launch_bwd_fast_t<__nv_bfloat16>(dS, bins, bin_sb, mask, gp, g_sb, status, B, V, D, G, pool, st);
+    return launch_bwd_fast_t<__nv_bfloat16>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, V, D, G, pool, st);
 }
 
 }  // namespace gvcnn

@@ -30,7 +30,8 @@ namespace gvcnn {
 template <typename T, int POOL, bool MASK, int V, int NCONS, int MINB>
 __global__ void __launch_bounds__(NCONS + kRingProducerThreads, MINB)
 pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
-                          const int64_t bin_sb, T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
+                          const int64_t bin_sb, const float *__restrict__ weights, const int64_t w_sb,
+                          T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
                           const int B, const int64_t D, const int G, const float fill,
                           const int tiles_per_shape, const int num_tiles, const int stages)
 {
@@ -105,6 +106,15 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
                 plans[s].first_mask = fm;
                 plans[s].tail_skip = (uint32_t)(G - 1 - last_bin);
             }
+            if (weights) {  // caller-supplied group weights (model.group_fusion's second argument; paper mode)
+                const float *wrow = weights + (int64_t)b * w_sb;
+                if (lane < V) plans[s].gw[k] = __ldg(wrow + bin);
+                if (lane == 0) {
+                    float sw = 0.0f;  // tf.reduce_sum(group_weight_list), left to right
+                    for (int g = 0; g < G; ++g) sw = __fadd_rn(sw, __ldg(wrow + g));
+                    plans[s].sumw = sw;
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full_bar[s], row_bytes * (uint32_t)V);
             __syncwarp();
@@ -131,13 +141,16 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         mbar_wait(&full_bar[s], ph);
 
         float acc[E];
-        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc);
+        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc,
+                                                        weights != nullptr);
+        const float sw_given = weights ? plans[s].sumw : 0.0f;
         // every lane of the warp is done reading the slot: hand it back to the producer
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
         if (active) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) acc[e] = div_by_rcp(acc[e], sumw, rcp_sumw);
+            for (int e = 0; e < E; ++e)
+                acc[e] = weights ? __fdiv_rn(acc[e], sw_given) : div_by_rcp(acc[e], sumw, rcp_sumw);
             stg_stream_16(S + out_off, Elem<T>::pack(acc));
         }
         b += step_b;
@@ -163,8 +176,8 @@ static int ring_sm_count()
 }
 
 template <typename T, int V, int NCONS, int MINB>
-static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
-                         uint8_t *mask, int32_t *status, int B, int64_t D, int G, int pool, float fill,
+static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb,
+                         const float *weights, int64_t w_sb, void *S, uint8_t *mask, int32_t *status, int B, int64_t D, int G, int pool, float fill,
                          cudaStream_t st)
 {
     constexpr int E = Elem<T>::kVec;
@@ -192,8 +205,8 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (err == cudaSuccess)                                                                              \
             err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
-                             bin_sb, static_cast<T *>(S), mask, status, B, D, G, fill, (int)tps,             \
-                             (int)tiles, stages);                                                            \
+                             bin_sb, weights, w_sb, static_cast<T *>(S), mask, status, B, D, G, fill,        \
+                             (int)tps, (int)tiles, stages);                                                  \
     } while (0)
     if (pool == GVCNN_POOL_MAX) {
         if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false);
@@ -206,36 +219,36 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
 }
 
 template <typename T>
-static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
-                         uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
+static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb,
+                         const float *weights, int64_t w_sb, void *S, uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
                          cudaStream_t st)
 {
     // the view counts of the reference's configurations (train.py:96 default 6; BASELINE sweep 6/12/20)
     // plus the other common multi-view rigs (4, 8, 16)
     if (D < 256 * Elem<T>::kVec) return -1000;  // tiles narrower than one consumer row: generic kernel
     switch (V) {
-    case 4: return launch_ring_v<T, 4, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 8: return launch_ring_v<T, 8, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);  // GVCNN paper: 8 / 12 views
-    case 12: return launch_ring_v<T, 12, 256, 2>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 16: return launch_ring_v<T, 16, 256, 1>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 20: return launch_ring_v<T, 20, 256, 1>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 4: return launch_ring_v<T, 4, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 8: return launch_ring_v<T, 8, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);  // GVCNN paper: 8 / 12 views
+    case 12: return launch_ring_v<T, 12, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 16: return launch_ring_v<T, 16, 256, 1>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 20: return launch_ring_v<T, 20, 256, 1>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
     default: return -1000;
     }
 }
 
 // returns -1000 when this fast path does not apply
-int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
-                              uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
+int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb,
+                              const float *weights, int64_t w_sb, void *S, uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool,
                               float fill, int dtype, cudaStream_t st)
 {
     if (V > 32 || G > 255) return -1000;
     if (dtype == GVCNN_F32) {
         if (D % 4) return -1000;
-        return launch_ring_t<float>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, st);
+        return launch_ring_t<float>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, V, D, G, pool, fill, st);
     }
     if (D % 8) return -1000;
-    return launch_ring_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, st);
+    return launch_ring_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, V, D, G, pool, fill, st);
 }
 
 }  // namespace gvcnn

@@ -14,6 +14,8 @@ struct __align__(16) RingPlan {
     uint32_t tail_skip;   // empty groups after the last non-empty one
     uint32_t pad[2];
     uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
+    float gw[32];         // caller-supplied weights only: weight of the group sorted view k is in
+    float sumw;           // caller-supplied weights only: sum of all G weights (left to right)
 };
 
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
@@ -40,7 +42,7 @@ template <typename T, int POOL, bool MASK, int V, uint32_t ROWSTRIDE>
 __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, const RingPlan &plan_s, const float fill,
                                                   const bool active, uint8_t *__restrict__ mask, const int B,
                                                   const int64_t D, const int64_t out_off,
-                                                  float (&acc)[Elem<T>::kVec])
+                                                  float (&acc)[Elem<T>::kVec], const bool wts = false)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
@@ -88,7 +90,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     }
                     float m[E];
                     Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
-                    const float w = (float)(1 + cnt);
+                    const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
                 }
@@ -149,7 +151,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                                 if (x[e] == m[e]) me[e] |= 1u << (k - j);
                         }
                     }
-                    const float w = (float)(1 + cnt);    // acc += w_g * P_g
+                    const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);  // acc += w_g * P_g
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);

@@ -12,6 +12,7 @@ W = ((torch.rand(V, Cr, device=dev) * 2 - 1) * 0.0765).requires_grad_(True)
 b = torch.zeros(V, device=dev, requires_grad=True)
 dS = torch.randn(B, D, device=dev)
 def step():
+    F.grad = W.grad = b.grad = None          # no gradient accumulation kernels in the timed loop
     S, *_ = model.grouping_fusion_paper(R, W, b, F, G)
     S.backward(dS)
 for _ in range(3): step()
