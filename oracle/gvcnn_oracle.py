@@ -273,7 +273,7 @@ def sorted_view_order(brow):
     return np.lexsort((np.arange(brow.size), brow))
 
 
-def pool_fuse_bwd(dS, F, bins, num_group, pool="max"):
+def pool_fuse_bwd(dS, F, bins, num_group, pool="max", weights=None):
     """dF [B, V, D] from dS [B, D].  Follows TF autodiff of model.py:62-100
     (SURVEY.md section 3.4), in TF's op order:
       div grad      g0 = dS / sum_w                     (_RealDivGrad)
@@ -298,6 +298,11 @@ def pool_fuse_bwd(dS, F, bins, num_group, pool="max"):
     uniq, inv = np.unique(bins, axis=0, return_inverse=True)
     inv = inv.reshape(-1)
     sumw = np.float32(num_group + V)
+    if weights is not None:                       # caller-supplied weights [G] (group_fusion's second argument)
+        weights = np.asarray(weights, dtype=np.float32)
+        sumw = np.float32(0)
+        for x in weights:
+            sumw = np.float32(sumw + x)
     for u, brow in enumerate(uniq):
         sel = np.where(inv == u)[0]
         g0 = dS[sel] / sumw
@@ -305,7 +310,7 @@ def pool_fuse_bwd(dS, F, bins, num_group, pool="max"):
             ind = np.where(brow == g)[0]
             if ind.size == 0:
                 continue
-            g1 = g0 * np.float32(1 + ind.size)
+            g1 = g0 * (np.float32(1 + ind.size) if weights is None else weights[g])
             if pool == "max":
                 x = F[sel][:, ind, :]                       # [n, k, D]
                 y = x.max(axis=1, keepdims=True)

@@ -774,3 +774,30 @@ def test_head_fold_gap(model):
     assert tuple(net.shape) == (N, Cf) and torch.equal(s1, s2)
     torch.testing.assert_close(net, S.reshape(N, -1, Cf).mean(dim=1), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(logits2, logits1, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("pool", ["max", "mean"])
+@pytest.mark.parametrize("V,D", [(12, 2048), (6, 1024), (5, 300)])
+def test_custom_weights_without_empty_fill_take_the_fast_kernels(model, pool, V, D):
+    """group_fusion's weights as given, empty groups contributing nothing (empty_fill = 0): the ring forward and
+    the V-templated backward read the per-shape weight row (the generic kernels for V = 5); bit-exact."""
+    B, G = 9, 8
+    F, bins, dS = make_inputs(V * 31 + D, B, V, D, G, ties=True)
+    row = bins[0]
+    w = np.random.default_rng(V).uniform(0.25, 3.0, G).astype(np.float32)
+    x = dev(F).requires_grad_(True)
+    S = model.pool_fuse(x, dev(row), G, pool=pool, empty_fill=0.0, group_weight=dev(w))
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[row, np.arange(V)] = 1
+    want = O.group_fusion(O.view_pooling([F[:, v] for v in range(V)], scheme, pool=pool, empty_fill=0.0), w)
+    np.testing.assert_array_equal(S.detach().cpu().numpy(), want)
+    S.backward(dev(dS))
+    np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, row, G, pool, weights=w))
+    # per-shape weight rows [B, G]
+    wb = np.random.default_rng(V + 1).uniform(0.25, 3.0, (B, G)).astype(np.float32)
+    S2 = model.pool_fuse(dev(F), dev(bins), G, pool=pool, empty_fill=0.0, group_weight=dev(wb))
+    for i in range(B):
+        sch = np.zeros((G, V), dtype=np.int32)
+        sch[bins[i], np.arange(V)] = 1
+        wi = O.group_fusion(O.view_pooling([F[i:i + 1, v] for v in range(V)], sch, pool=pool, empty_fill=0.0), wb[i])
+        np.testing.assert_array_equal(S2[i:i + 1].cpu().numpy(), wi)
