@@ -188,11 +188,84 @@ def main():
             flat["%s__%s" % (cname, k)] = v
     np.savez(os.path.join(HERE, "ref_graph_pool_fuse.npz"), **flat)
 
+    # ---- the whole head: the reference's own gvcnn() (nets/model.py:105-166) run end to end, twice, exactly
+    #      like train.py:264-288 drives it: first for the view scores, then - after its own group_scheme /
+    #      group_weight on the host - for the shape descriptor and the logits.  The backbone is a stub that
+    #      hands out pre-generated block3 / block4 maps; the Keras layers are NumPy stand-ins with seeded
+    #      weights (Dense(1) per view inside the loop, model.py:145; Dense(num_classes) at :164).
+    head_cases = {}
+    for name, (V, N, hw3, C3, hw4, C4, ncls) in {"head_v6": (6, 4, 3, 64, 2, 128, 5),
+                                                  "head_v12": (12, 3, 2, 96, 1, 256, 7)}.items():
+        feats3 = [rng.standard_normal((N, hw3, hw3, C3)).astype(np.float32) for _ in range(V)]
+        feats4 = [np.maximum(rng.standard_normal((N, hw4, hw4, C4)), 0).astype(np.float32) for _ in range(V)]
+        lim = np.sqrt(6.0 / (C3 + 1))
+        dense_w = [rng.uniform(-lim, lim, (C3, 1)).astype(np.float32) for _ in range(V)]
+        dense_b = [np.float32(rng.uniform(-3, 3)) for _ in range(V)]         # spread the batch-mean scores
+        cls_w = (rng.standard_normal((C4, ncls)) * 0.05).astype(np.float32)
+        cls_b = np.zeros(ncls, dtype=np.float32)
+        state = {"view": 0, "dense": 0}
+
+        class _Inputs(np.ndarray):                                            # inputs.get_shape().as_list()
+            def get_shape(self):
+                return types.SimpleNamespace(as_list=lambda: list(self.shape))
+
+        def resnet_v2_50(batch_view, num_classes=None, is_training=None, reuse=None):
+            v = state["view"]
+            state["view"] += 1
+            return None, {"resnet_v2_50/block3": feats3[v], "resnet_v2_50/block4": feats4[v]}
+
+        class _GAP:
+            def __call__(self, x):
+                return np.asarray(x, dtype=np.float32).mean(axis=(1, 2), dtype=np.float32)
+
+        class _Dense:
+            def __init__(self, units):
+                i = state["dense"]
+                state["dense"] += 1
+                self.k, self.b = (dense_w[i], dense_b[i]) if units == 1 else (cls_w, cls_b)
+
+            def __call__(self, x):
+                return (np.asarray(x, dtype=np.float32) @ self.k + self.b).astype(np.float32)
+
+        import contextlib
+        tfm = sys.modules["tensorflow"]
+        tfm.transpose = lambda x, perm: np.transpose(np.asarray(x), perm)
+        tfm.reduce_mean = lambda x: np.float32(np.asarray(x, dtype=np.float32).mean(dtype=np.float32))
+        tfm.nn = types.SimpleNamespace(sigmoid=lambda x: np.float32(1) / (np.float32(1) + np.exp(-x, dtype=np.float32)))
+        tfm.math = types.SimpleNamespace(log=lambda x: np.log(x, dtype=np.float32))
+        tfm.keras = types.SimpleNamespace(layers=types.SimpleNamespace(GlobalAveragePooling2D=_GAP, Dense=_Dense))
+        ref.slim = types.SimpleNamespace(arg_scope=lambda scope: contextlib.nullcontext())
+        ref.resnet_v2 = types.SimpleNamespace(resnet_arg_scope=lambda: None, resnet_v2_50=resnet_v2_50)
+        images = np.zeros((N, V, 4, 4, 3), dtype=np.float32).view(_Inputs)   # the stub backbone ignores pixels
+
+        def run(scheme, weight):
+            state["view"] = state["dense"] = 0
+            return ref.gvcnn(images, ncls, scheme, weight, is_training=False, dropout_keep_prob=1.0)
+
+        G = 10
+        scores, _, _ = run(np.zeros((G, V), dtype=np.int32), np.ones(G, dtype=np.float32))    # partial_run #1
+        scheme = ref.group_scheme([scores], G, V)                                             # train.py:277
+        weight = ref.group_weight(scheme)                                                     # train.py:278
+        scores2, shape_descriptor, logits = run(scheme, weight)                               # partial_run #2
+        assert all(a == b for a, b in zip(scores, scores2))
+        head_cases[name] = dict(
+            R=np.stack([f.mean(axis=(1, 2), dtype=np.float32) for f in feats3], axis=1),      # [N, V, C3] post-GAP
+            W=np.stack([k[:, 0] for k in dense_w]), b=np.asarray(dense_b, dtype=np.float32),
+            F=np.stack(feats4), scores=np.asarray(scores, dtype=np.float32),
+            scheme=np.asarray(scheme, dtype=np.int32), weight=weight,
+            shape_descriptor=shape_descriptor, logits=logits, cls_w=cls_w, cls_b=cls_b)
+    flat = {}
+    for cname, d in head_cases.items():
+        for k, v in d.items():
+            flat["%s__%s" % (cname, k)] = v
+    np.savez(os.path.join(HERE, "ref_graph_head.npz"), **flat)
+    print("head scores:", head_cases["head_v6"]["scores"], "bins:", np.argmax(head_cases["head_v6"]["scheme"], axis=0))
+
     with open(os.path.join(HERE, "ref_graph_meta.json"), "w") as f:
         json.dump({"generated_by": "tests/golden/make_golden.py",
                    "reference": "ace19-dev/gvcnn-tf nets/model.py (group_scheme, group_weight, "
                                 "view_pooling, group_fusion run unmodified over a NumPy stand-in for TF ops)",
-                   "errors": errs, "cases": sorted(cases)}, f, indent=1)
+                   "errors": errs, "cases": sorted(cases), "head_cases": sorted(head_cases)}, f, indent=1)
     print("errors:", errs)
     print("kat2 S:", cases["kat2"]["S"], "w:", cases["kat2"]["w"])
 

@@ -801,3 +801,29 @@ def test_custom_weights_without_empty_fill_take_the_fast_kernels(model, pool, V,
         sch[bins[i], np.arange(V)] = 1
         wi = O.group_fusion(O.view_pooling([F[i:i + 1, v] for v in range(V)], sch, pool=pool, empty_fill=0.0), wb[i])
         np.testing.assert_array_equal(S2[i:i + 1].cpu().numpy(), wi)
+
+
+@pytest.mark.parametrize("case", ["head_v6", "head_v12"])
+def test_reference_gvcnn_head_end_to_end(model, golden_dir, case):
+    """Golden vectors from the reference's own gvcnn() + group_scheme + group_weight (tests/golden/
+    make_golden.py): the CUDA path in the literal batch-mean mode reproduces its scores (to float32 rounding),
+    its scheme and weights exactly and its shape descriptor bit for bit; logits follow."""
+    z = np.load(os.path.join(golden_dir, "ref_graph_head.npz"))
+    g = {k: z["%s__%s" % (case, k)] for k in ("R", "W", "b", "F", "scores", "scheme", "weight", "shape_descriptor",
+                                               "logits", "cls_w", "cls_b")}
+    G, V = g["scheme"].shape
+    raw = dev(g["R"])
+    finals = [dev(g["F"][v]) for v in range(V)]
+    scores = model.view_scores(raw, dev(g["W"]), dev(g["b"]))                       # nets/model.py:144-148
+    np.testing.assert_allclose(scores.cpu().numpy()[0], g["scores"], rtol=2e-6, atol=2e-7)
+    scheme = model.group_scheme([scores[0]], G, V)                                   # train.py:277
+    np.testing.assert_array_equal(scheme.cpu().numpy(), g["scheme"])
+    weight = model.group_weight(scheme)                                              # train.py:278
+    np.testing.assert_array_equal(weight.cpu().numpy(), g["weight"])
+    S = model.group_fusion(model.view_pooling(finals, scheme), weight)               # nets/model.py:154-157
+    np.testing.assert_array_equal(S.cpu().numpy(), g["shape_descriptor"])
+    # the single-pass form gives the same descriptor
+    S2, sr = model.grouping_fusion(raw, dev(g["W"]), dev(g["b"]), finals, G, score_reduce="batch")
+    assert torch.equal(S2, S)
+    logits = S.mean(dim=(1, 2)) @ dev(g["cls_w"]) + dev(g["cls_b"])                 # nets/model.py:163-164
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-5, atol=1e-6)

@@ -218,3 +218,25 @@ def test_graph_literal_cpu_baseline_matches():
     out = O.grouping_fusion_fwd(R, W, b, np.ascontiguousarray(F.transpose(1, 0, 2)), G, score_reduce="batch",
                                 score_dtype=np.float32)
     np.testing.assert_allclose(S, out["S"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["head_v6", "head_v12"])
+def test_reference_gvcnn_head_end_to_end(golden_dir, case):
+    """The reference's own gvcnn() (nets/model.py:105-166) driven like train.py:264-288 (scores -> its
+    group_scheme / group_weight -> shape descriptor, logits) over a stub backbone and NumPy Keras layers:
+    the oracle reproduces its scores (float32 rounding of the dot product aside), its scheme and weights
+    exactly, and its shape descriptor bit for bit."""
+    z = np.load(os.path.join(golden_dir, "ref_graph_head.npz"))
+    g = {k: z["%s__%s" % (case, k)] for k in ("R", "W", "b", "F", "scores", "scheme", "weight", "shape_descriptor",
+                                               "logits", "cls_w", "cls_b")}
+    G, V = g["scheme"].shape
+    x, s = O.view_scores(g["R"], g["W"], g["b"], score_reduce="batch", dtype=np.float64)
+    np.testing.assert_allclose(s[0], g["scores"], rtol=2e-6, atol=2e-7)   # batch mean cancels: absolute float32 error
+    np.testing.assert_array_equal(O.bins_from_scores(s[0].astype(np.float32), G), np.argmax(g["scheme"], axis=0))
+    scheme = O.group_scheme([list(g["scores"])], G, V)
+    np.testing.assert_array_equal(scheme, g["scheme"])
+    np.testing.assert_array_equal(O.group_weight(scheme), g["weight"])
+    S = O.group_fusion(O.view_pooling([g["F"][v] for v in range(V)], scheme), O.group_weight(scheme))
+    np.testing.assert_array_equal(S, g["shape_descriptor"])
+    logits = S.mean(axis=(1, 2), dtype=np.float32) @ g["cls_w"] + g["cls_b"]
+    np.testing.assert_allclose(logits, g["logits"], rtol=1e-5, atol=1e-6)
