@@ -248,7 +248,10 @@ def main():
         weight = ref.group_weight(scheme)                                                     # train.py:278
         scores2, shape_descriptor, logits = run(scheme, weight)                               # partial_run #2
         assert all(a == b for a, b in zip(scores, scores2))
+        state["view"] = state["dense"] = 0
+        basic_descriptor, _ = ref.basic(images, ncls, is_training=False, dropout_keep_prob=1.0)   # model.py:169-206
         head_cases[name] = dict(
+            basic_descriptor=basic_descriptor,
             R=np.stack([f.mean(axis=(1, 2), dtype=np.float32) for f in feats3], axis=1),      # [N, V, C3] post-GAP
             W=np.stack([k[:, 0] for k in dense_w]), b=np.asarray(dense_b, dtype=np.float32),
             F=np.stack(feats4), scores=np.asarray(scores, dtype=np.float32),

@@ -827,3 +827,50 @@ def test_reference_gvcnn_head_end_to_end(model, golden_dir, case):
     assert torch.equal(S2, S)
     logits = S.mean(dim=(1, 2)) @ dev(g["cls_w"]) + dev(g["cls_b"])                 # nets/model.py:163-164
     np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    # the reference's basic() (nets/model.py:169-206)
+    np.testing.assert_array_equal(model.basic_pool(finals).cpu().numpy(), z["%s__basic_descriptor" % case])
+
+
+def test_seeded_fuzz_against_oracle(model, c_oracle):
+    """70 random configurations (views, groups, descriptor length, layout, dtype, pool, fill, shared or per-shape
+    scheme): forward and backward against the C oracle."""
+    rng = np.random.default_rng(20261017)
+    for it in range(70):
+        V = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 16, 20, 31, 32, 33, 48, 80]))
+        G = int(rng.choice([1, 2, 3, 8, 10, 16, 40]))
+        D = int(rng.choice([1, 3, 4, 8, 60, 256, 1000, 1024, 1032, 2048, 2056, 4096]))
+        B = int(rng.integers(1, 9))
+        pool = str(rng.choice(["max", "mean"]))
+        fill = float(rng.choice([0.0, 1.0, -2.5]))
+        layout = str(rng.choice(["bvd", "vbd", "list"]))
+        bf16 = bool(rng.integers(0, 2)) and D % 8 == 0
+        shared = bool(rng.integers(0, 2))
+        F = np.maximum(np.round(rng.standard_normal((B, V, D)) * 4) / 4, -0.5).astype(np.float32)
+        dS = rng.standard_normal((B, D)).astype(np.float32)
+        bins = rng.integers(0, G, (V,) if shared else (B, V)).astype(np.int32)
+        td = torch.bfloat16 if bf16 else torch.float32
+        if bf16:
+            F, dS = O.round_bf16(F), O.round_bf16(dS)
+        if layout == "bvd":
+            x = [dev(F, td).requires_grad_(True)]
+            S = model.pool_fuse(x[0], dev(bins), G, pool=pool, empty_fill=fill)
+        elif layout == "vbd":
+            x = [dev(F.transpose(1, 0, 2), td).requires_grad_(True)]
+            S = model.pool_fuse(x[0], dev(bins), G, pool=pool, empty_fill=fill, layout="vbd")
+        else:
+            x = [dev(F[:, v], td).requires_grad_(True) for v in range(V)]
+            S = model.pool_fuse(x, dev(bins), G, pool=pool, empty_fill=fill)
+        S.backward(dev(dS, td))
+        want = c_oracle.pool_fuse_fwd(F, bins, G, pool, fill)
+        wantg = c_oracle.pool_fuse_bwd(dS, F, bins, G, pool)
+        if bf16:
+            want, wantg = O.round_bf16(want), O.round_bf16(wantg)
+        tag = "it=%d V=%d G=%d D=%d B=%d %s fill=%s %s bf16=%s shared=%s" % (it, V, G, D, B, pool, fill, layout, bf16, shared)
+        np.testing.assert_array_equal(S.detach().float().cpu().numpy(), want, err_msg=tag)
+        if layout == "bvd":
+            got = x[0].grad.float().cpu().numpy()
+        elif layout == "vbd":
+            got = x[0].grad.float().cpu().numpy().transpose(1, 0, 2)
+        else:
+            got = np.stack([t.grad.float().cpu().numpy() for t in x], axis=1)
+        np.testing.assert_array_equal(got, wantg, err_msg=tag)

@@ -240,3 +240,7 @@ def test_reference_gvcnn_head_end_to_end(golden_dir, case):
     np.testing.assert_array_equal(S, g["shape_descriptor"])
     logits = S.mean(axis=(1, 2), dtype=np.float32) @ g["cls_w"] + g["cls_b"]
     np.testing.assert_allclose(logits, g["logits"], rtol=1e-5, atol=1e-6)
+    # basic() (nets/model.py:169-206): plain max over all views = one group, unit weight
+    basic = z["%s__basic_descriptor" % case]
+    one = O.group_fusion(O.view_pooling([g["F"][v] for v in range(V)], np.ones((1, V), dtype=np.int64)), np.ones(1))
+    np.testing.assert_array_equal(one, basic)
