@@ -173,7 +173,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "grouping+fusion forward, 12 views, D=2048, G=8, C_raw=1024, fp32 "
                                "(BASELINE.json configs[1]); each step = a bounded sample of %d of the 4096 shapes" % B,
                    "B_per_step": B, "V": CFG["V"], "D": CFG["D"], "G": CFG["G"], "C_raw": CFG["C_raw"],
@@ -214,9 +214,13 @@ def run_cuda_arm(args):
     C.check(L.gvcnn_check_device(), "gvcnn_check_device")
 
     B, V, D, G, Cr = CFG["B"], CFG["V"], CFG["D"], CFG["G"], CFG["C_raw"]
+    if args.scaling == "strong":                                     # B_total fixed at 4096
+        if B % world:
+            raise SystemExit("bench.py: --scaling strong needs %d %% n_gpus == 0" % B)
+        B //= world
     K, Wm = args.steps, args.warmup
     s = 4
-    NSETS = 2                                                        # rotate input sets (each set >> 126 MB L2)
+    NSETS = 2 if args.scaling == "weak" else 2 * world               # rotating input sets: 1.2 GB in total >> 126 MB L2
     sets = []
     host = None
     for i in range(NSETS):
@@ -379,6 +383,14 @@ def run_cuda_arm(args):
     barrier()
     t_pool_m = statistics.mean(e[1].elapsed_time(e[2]) for e in evb)
     t_bwd = statistics.mean(e[2].elapsed_time(e[3]) for e in evb)
+    # ... and the gradient all-reduce alone (N > 1): K back-to-back collectives, nothing to hide behind
+    us_allreduce = None
+    if world > 1:
+        def step_allreduce(i):
+            dist.all_reduce(grad_bucket, op=dist.ReduceOp.AVG)
+        for i in range(3):
+            step_allreduce(i)
+        us_allreduce = timed(step_allreduce, K) / K * 1e3
 
     # ---- the reference-literal mode (one scheme per batch, nets/model.py:146): x per (shape, view), deterministic
     #      column sums, V scores/bins, pooling with the shared bin row.  Reported beside the per-shape headline.
@@ -463,15 +475,17 @@ def run_cuda_arm(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-        "ms_per_step": ms_fwd / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_fwd / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "grouping+fusion forward (score+bin, pool+fuse), 12 views, D=2048, G=8, "
-                               "B=4096 shapes per GPU, C_raw=1024, fp32 (BASELINE.json configs[1])",
+                               "B=%d shapes per GPU, C_raw=1024, fp32 (BASELINE.json configs[1]%s)"
+                               % (B, "" if args.scaling == "weak" else "; strong scaling: 4096 shapes split over the ranks"),
                    "B_per_gpu": B, "V": V, "D": D, "G": G, "C_raw": Cr, "pool": CFG["pool"],
                    "empty_fill": CFG["empty_fill"], "score_reduce": "shape", "parallelism": "shape-sharded x%d" % world,
                    "launch": ("CUDA graph of %d steps replayed K/%d times" % (NSETS, NSETS)) if graph_fwd is not None
                              else "stream launches",
-                   "l2": "inputs larger than L2 (F 403 MB + R 201 MB per step vs 126 MB) and %d rotating input sets" % NSETS},
+                   "l2": "inputs larger than L2 (F %.0f MB + R %.0f MB per step vs 126 MB) and %d rotating input sets"
+                         % (B * V * D * s / 1e6, B * V * Cr * s / 1e6, NSETS)},
         "roofline": ({"bound": "hbm", "kernel": "fused_fwd_kernel (score+bin+pool+fuse, one launch per step)",
                       "achieved": ach_fused, "peak": peak, "unit": "GB/s", "frac": ach_fused / peak, "traffic": traffic,
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["fwd"], "us_per_launch": t_fused * 1e3}
@@ -495,7 +509,8 @@ def run_cuda_arm(args):
                                                          "overlapped with the backward" % grad_bucket.numel()
                                                          if world > 1 else "no collective at N=1"),
                     "value": world * B * K / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / K,
-                    "algorithmic_GBps_per_gpu": ach_train_step, "frac_of_peak": ach_train_step / peak},
+                    "algorithmic_GBps_per_gpu": ach_train_step, "frac_of_peak": ach_train_step / peak,
+                    "allreduce_alone_us": us_allreduce},
         "literal_batch_mode": {"workload": "same batch, reference-literal score_reduce='batch' (one scheme per batch, "
                                            "nets/model.py:146): 4 launches", "value": world * B * K / (ms_literal * 1e-3),
                                "unit": UNIT, "ms_per_step": ms_literal / K},
@@ -530,6 +545,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 4096 shapes per GPU (default, the contract's line); strong: 4096 shapes in total")
     ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of a CUDA graph")
     args = ap.parse_args()
     if args.steps < 1:

@@ -12,7 +12,8 @@ constexpr int kRingProducerThreads = 32;
 struct __align__(16) RingPlan {
     uint32_t first_mask;  // bit k: the k-th sorted view starts a group
     uint32_t tail_skip;   // empty groups after the last non-empty one
-    uint32_t pad[2];
+    int32_t b;            // shape of the tile in this slot; -1 = no more tiles (pool_fwd_ring.cu, dynamic walk)
+    int32_t tile;         // tile index within the shape
     uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
     float gw[32];         // caller-supplied weights only: weight of the group sorted view k is in
     float sumw;           // caller-supplied weights only: sum of all G weights (left to right)

@@ -573,6 +573,36 @@ def test_streams_are_independent(model):
         np.testing.assert_array_equal(a.cpu().numpy(), w2)
 
 
+@pytest.mark.timeout(300)
+def test_dynamic_tile_handout_with_colliding_launches(model):
+    """Long tile walks draw their tiles from a per-launch counter slot (pool_fwd_ring.cu, TileSlot; slot =
+    launch ticket % 64).  Queue 64 launches on each of two streams behind a spin kernel so that launch k of
+    stream A and launch k of stream B (tickets 64 apart: the same slot) contend for SMs at the same time, with
+    different inputs, masks on one side only; every result must still be the oracle's, bit for bit."""
+    B, V, D, G = 1024, 12, 2048, 8                       # 2048 tiles >= 6 rounds of 296 CTAs: dynamic walk
+    F1, b1, _ = make_inputs(11, B, V, D, G)
+    F2, b2, _ = make_inputs(12, B, V, D, G, ties=True)
+    x1, x2, bb1, bb2 = dev(F1), dev(F2), dev(b1), dev(b2)
+    x2.requires_grad_(True)                              # stream B runs the tie-mask variant of the kernel
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outsA, outsB = [], []
+    with torch.cuda.stream(sA):
+        torch.cuda._sleep(200_000_000)                   # ~0.1 s: both queues fill before anything runs
+        for _ in range(64):
+            outsA.append(model.pool_fuse(x1, bb1, G))
+    with torch.cuda.stream(sB):
+        torch.cuda._sleep(200_000_000)
+        for _ in range(64):
+            outsB.append(model.pool_fuse(x2, bb2, G))
+    torch.cuda.synchronize()
+    w1, w2 = O.pool_fuse_fwd(F1, b1, G), O.pool_fuse_fwd(F2, b2, G)
+    for a in outsA:
+        np.testing.assert_array_equal(a.cpu().numpy(), w1)
+    for a in outsB:
+        np.testing.assert_array_equal(a.detach().cpu().numpy(), w2)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
 @pytest.mark.parametrize("D", [1024, 2048])
