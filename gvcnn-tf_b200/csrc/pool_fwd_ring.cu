@@ -119,8 +119,17 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         }
         mbar_fence_init();
     }
+    // The producer warp does not need the barriers to fetch its first bins: it passes the dependency wait
+    // and issues that load while thread 0 is still initialising them.  Nothing touches global memory
+    // before pdl_wait(); the consumers' first global access (a store) comes after a full barrier, i.e. after
+    // the producer's wait, and they wait themselves as well.
+    int nb = 0x7fffffff;
+    if ((int)threadIdx.x >= NCONS) {
+        pdl_wait();
+        if ((int)(threadIdx.x & 31) < V) nb = __ldg(bins + (int64_t)b * bin_sb + (threadIdx.x & 31));
+    }
     __syncthreads();
-    pdl_wait();                // nothing above touches global memory
+    pdl_wait();
     pdl_launch_dependents();
     if (threadIdx.x == 0) GVCNN_RING_MARK(4);
 
@@ -133,8 +142,6 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         // after (its index is fetched from the counter behind this tile's work).  Indices only grow.
         int t = blockIdx.x;
         int t1 = (int)min((int64_t)blockIdx.x + (int64_t)gridDim.x, (int64_t)num_tiles);
-        int nb = 0x7fffffff;
-        if (t < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b * bin_sb + lane);
         if (dynamic && lane == 0) tile_slot_claim(slot, ticket);
         while (t < num_tiles) {
             const int64_t d0 = (int64_t)tile * TD;

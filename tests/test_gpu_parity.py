@@ -573,6 +573,31 @@ def test_streams_are_independent(model):
         np.testing.assert_array_equal(a.cpu().numpy(), w2)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
+@pytest.mark.parametrize("V", [6, 12, 20])
+def test_long_walks_every_ring_variant(model, c_oracle, V, pool, fill, dtype):
+    """B = 2048 gives every instantiation of the ring kernel (two CTAs per SM at V <= 12, one at V = 20; packed
+    bf16; tie mask; mean) a walk of >= 6 rounds, i.e. the dynamic tile hand-out with re-used ring slots:
+    forward, tie mask -> backward, bit-exact against the C oracle."""
+    B, D, G = 2048, 2048, 8
+    F, bins, dS = make_inputs(V * 7 + (dtype == "bf16"), B, V, D, G, ties=True)
+    if dtype == "bf16":
+        F, dS = O.round_bf16(F), O.round_bf16(dS)
+        td = torch.bfloat16
+    else:
+        td = torch.float32
+    x = dev(F, td).requires_grad_(True)
+    S = model.pool_fuse(x, dev(bins), G, pool=pool, empty_fill=fill)
+    S.backward(dev(dS, td))
+    want = c_oracle.pool_fuse_fwd(F, bins, G, pool, fill)
+    wantg = c_oracle.pool_fuse_bwd(dS, F, bins, G, pool)
+    if dtype == "bf16":
+        want, wantg = O.round_bf16(want), O.round_bf16(wantg)
+    np.testing.assert_array_equal(S.detach().float().cpu().numpy(), want)
+    np.testing.assert_array_equal(x.grad.float().cpu().numpy(), wantg)
+
+
 @pytest.mark.timeout(300)
 def test_dynamic_tile_handout_with_colliding_launches(model):
     """Long tile walks draw their tiles from a per-launch counter slot (pool_fwd_ring.cu, TileSlot; slot =
