@@ -172,7 +172,8 @@ def main(argv=None):
         if rank == 0:
             print("Epoch #%d, rate %.6f, train loss %.5f, val top1_acc %.3f%%" % (epoch, lr, history[-1][1], 100 * acc))
             os.makedirs(flags.train_logdir, exist_ok=True)
-            torch.save({"head": head.state_dict(), "opt": opt.state_dict(), "epoch": epoch, "global_step": global_step},
+            torch.save({"head": head.state_dict(), "opt": opt.state_dict(), "epoch": epoch, "global_step": global_step,
+                        "flags": vars(flags)},
                        os.path.join(flags.train_logdir, "%s-%04d" % (flags.ckpt_name_to_save, epoch)))
     if rank == 0 and history:
         print("confusion matrix (last epoch):\n%s" % cm)

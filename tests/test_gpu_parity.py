@@ -507,7 +507,8 @@ def test_many_views_chunked_forward(model, pool, fill, B, V, D, G):
 
 def test_train_head_driver_learns_and_resumes(model, tmp_path):
     """the train.py-shaped driver (same flags / LR policy / per-epoch checkpoints) trains the
-    head on synthetic features, in the reference-literal mode and in paper mode, and resumes."""
+    head on synthetic features, in the reference-literal mode and in paper mode, and resumes; the eval.py-shaped
+    driver restores its newest checkpoint and reproduces its validation accuracy."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("train_head", os.path.join(root, "gvcnn-tf_b200", "train_head.py"))
@@ -525,7 +526,25 @@ def test_train_head_driver_learns_and_resumes(model, tmp_path):
         h2 = th.main(common + extra + ["--how_many_training_epochs", "4", "--train_logdir", logdir,
                                        "--saved_checkpoint_dir", logdir])
         assert [e for e, _, _ in h2] == [3]                  # resumed after epoch 2
+        # eval.py-shaped driver: newest checkpoint of the directory, same validation features -> same accuracy;
+        # the same features through a feature shard on disk -> the same predictions
+        spec_e = importlib.util.spec_from_file_location("eval_head", os.path.join(root, "gvcnn-tf_b200", "eval_head.py"))
+        eh = importlib.util.module_from_spec(spec_e)
+        spec_e.loader.exec_module(eh)
+        ev = eh.main(["--checkpoint_path", logdir, "--num_views", "6", "--batch_size", "8",
+                      "--dataset_path", str(tmp_path / "absent")])
+        assert ev["n"] == 24 and abs(ev["per_shape_accuracy"] - h2[-1][2]) < 1e-12
+        assert int(ev["confusion_matrix"].sum()) == 24
+        fl_t = th.build_flags().parse_args(common + extra)
+        src = th.SyntheticFeatures(24, fl_t, 5, fl_t.seed + 2, "cpu")
+        from gvcnn_tf_b200 import records
+        prefix = str(tmp_path / (mode + "_val"))
+        records.write_feature_shard(prefix, src.raw.numpy(), src.final.numpy(), src.labels.numpy())
+        ev2 = eh.main(["--checkpoint_path", logdir, "--num_views", "6", "--batch_size", "8", "--dataset_path", prefix])
+        assert torch.equal(ev2["confusion_matrix"], ev["confusion_matrix"]) and ev2["accuracy"] == ev["accuracy"]
     fl = th.build_flags().parse_args([])
+    fe = eh.build_flags().parse_args([])
+    assert fe.batch_size == 4 and fe.num_views == 6 and fe.height == 299 and fe.num_group == 10       # eval.py:37-40
     assert fl.num_views == 6 and fl.num_group == 10 and fl.batch_size == 4 and fl.momentum == 0.9   # train.py:94-97
     assert abs(th.learning_rate(fl, 0) - 0.001) < 1e-12 and th.learning_rate(fl, 300000) == 0.0
 
