@@ -213,6 +213,26 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float rcp_b)
     return __fdiv_rn(a, b);
 }
 
+// Group mean = sum / n (tf.reduce_mean: Eigen's MeanReducer divides the sum by the count), exactly, with
+// the division left out where it is free: n == 1 (most groups once G is comparable to V) returns the sum, a
+// power of two multiplies by the exactly representable 2^-k (RN(x * 2^-k) == RN(x / 2^k) for every x,
+// subnormal results included), anything else is the IEEE division.  n is warp-uniform at every call site, so
+// the branches do not diverge.
+template <int E>
+__device__ __forceinline__ void mean_of_sum(float (&m)[E], const int n)
+{
+    if (n <= 1) return;
+    if ((n & (n - 1)) == 0) {
+        const float r = __uint_as_float((uint32_t)(127 - (31 - __clz(n))) << 23);  // 2^-log2(n)
+#pragma unroll
+        for (int e = 0; e < E; ++e) m[e] = __fmul_rn(m[e], r);
+    } else {
+        const float fn = (float)n;
+#pragma unroll
+        for (int e = 0; e < E; ++e) m[e] = __fdiv_rn(m[e], fn);
+    }
+}
+
 // ---- element packing ---------------------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {

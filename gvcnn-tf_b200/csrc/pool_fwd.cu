@@ -126,11 +126,9 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
             for (int e = 0; e < E; ++e) m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
         }
         const float w = plan.gw[k];
+        if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, len);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)len);
-            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-        }
+        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
         if (Pout) {
             T *pp = Pout + ((int64_t)g * B) * D + out_off;
             if constexpr (VEC) stg_stream_16(pp, Elem<T>::pack(m));
@@ -281,11 +279,9 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
         }
     };
     auto close_group = [&]() {  // acc += w_g * P_g for the group that just ended
+        if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, (int)len);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)len);
-            acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-        }
+        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
         if (Pout && active) stg_stream_16(Pout + ((int64_t)cur_g * B) * D + out_off, Elem<T>::pack(m));
         prev_g = cur_g;
     };

@@ -1,8 +1,9 @@
 // Pooling + fusion forward, fast path: persistent, warp-specialised, TMA-fed ring.
 //
 // Same arithmetic and op order as pool_fwd.cu (nets/model.py:28-102; see there),
-// different plumbing.  Resident CTAs (one or two per SM) walk tiles (tile = TD
-// consecutive descriptor elements of one shape, all V views).  Roles:
+// different plumbing.  One CTA per SM stays resident and walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = TD consecutive descriptor
+// elements of one shape, all V views).  Roles:
 //   * producer warp: prefetches the shape's V bins, ranks the views by
 //     (bin, view) with warp shuffles, waits for a free ring slot, publishes the
 //     per-tile plan, and then lanes 0..V-1 each fire ONE 1-D bulk async copy
@@ -14,13 +15,15 @@
 //     the division and the streaming store.
 // The ring (4 slots x 48 KB at V = 12, fp32) keeps ~150-190 KB of loads in
 // flight per SM continuously; there is no per-tile prologue bubble and no
-// wave tail.  Tiles are handed out dynamically after two static rounds (see
-// TileSlot below) so the CTAs, which stream at slightly different rates, all
-// run dry within one tile time of each other.  Used when rows are 16-byte
-// aligned, V is one of the instantiated view counts and no per-group
-// descriptors are requested; every other case takes the generic kernel in
-// pool_fwd.cu.
-#include <atomic>
+// wave tail.  Used when rows are 16-byte aligned, V is one of the instantiated
+// view counts and no per-group descriptors are requested; every other case
+// takes the generic kernel in pool_fwd.cu.
+//
+// The tile walk is static (t = blockIdx.x, blockIdx.x + gridDim.x, ...).  A dynamic hand-out from a per-launch
+// counter was built and measured: it shortens the spread of CTA end times (median idle 3 -> 1.2 us
+// in scripts/ring_trace_probe.cu) but is neutral to slower once launches run back to back, and slower for small
+// tiles (V = 6) and shallow rings (V = 20) because the compiler emits the one-lane atomic in its warp-aggregated
+// form, which waits for the counter on the spot.
 #include <cstdlib>
 
 #include "ring_common.cuh"
@@ -42,53 +45,18 @@ __device__ unsigned long long g_ring_trace[8 * 1024];
 #define GVCNN_RING_MARK(slot_) do { } while (0)
 #endif
 
-// ---- dynamic tile hand-out ------------------------------------------------------------------------
-// The first two rounds of tiles are static (t = blockIdx.x, blockIdx.x + gridDim.x); every later tile
-// comes from a per-launch counter.  The library owns no per-launch memory, so the counter lives in a small
-// table of device-global slots and a launch finds its slot by a ticket the host draws from a process-wide
-// counter (unique per launch call; a replayed graph node repeats its ticket, but a graph never overlaps
-// itself).  Slot = ticket % kTileSlots.  A CTA claims the slot with compare-and-swap (0 -> ticket) or finds
-// its own ticket there; if another live launch holds it, it waits - that launch never waits for anything
-// and its resident CTAs drain all of its tiles, so this cannot deadlock.  The last CTA to finish puts the
-// slot back to zero.  ticket == 0 selects the fully static walk (t += gridDim.x).
-struct TileSlot {
-    unsigned long long key;  // 0 = free, else the owning launch's ticket
-    unsigned int next;       // tiles handed out beyond the static rounds
-    unsigned int done;       // CTAs of the owning launch that have finished
-};
-constexpr int kTileSlots = 64;
-__device__ TileSlot g_tile_slots[kTileSlots];
-
-__device__ __forceinline__ void tile_slot_claim(TileSlot *slot, unsigned long long ticket)
-{
-    for (;;) {
-        const unsigned long long cur = atomicCAS(&slot->key, 0ull, ticket);
-        if (cur == 0ull || cur == ticket) return;
-        __nanosleep(256);
-    }
-}
-__device__ __forceinline__ void tile_slot_finish(TileSlot *slot, unsigned int ctas)
-{
-    __threadfence();
-    if (atomicAdd(&slot->done, 1u) == ctas - 1u) {  // every other CTA has its last tile index already
-        atomicExch(&slot->next, 0u);
-        atomicExch(&slot->done, 0u);
-        __threadfence();
-        atomicExch(&slot->key, 0ull);
-    }
-}
-
 // V and the consumer count are compile-time: rows sit at immediate offsets, every loop over views is
 // fully unrolled, and the only data-dependent control flow left is one uniform branch per view
-// ("does this view start a group?").  MINB = CTAs per SM the register budget is sized for.
-template <typename T, int POOL, bool MASK, int V, int NCONS, int MINB>
+// ("does this view start a group?").  MINB = CTAs per SM the register budget is sized for.  WTS = the caller
+// supplies the group weights (model.group_fusion's second argument, paper mode); the default instantiation
+// carries none of that code.
+template <typename T, int POOL, bool MASK, bool WTS, int V, int NCONS, int MINB>
 __global__ void __launch_bounds__(NCONS + kRingProducerThreads, MINB)
 pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
                           const int64_t bin_sb, const float *__restrict__ weights, const int64_t w_sb,
                           T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
                           const int B, const int64_t D, const int G, const float fill,
-                          const int tiles_per_shape, const int num_tiles, const int stages,
-                          const unsigned long long ticket)
+                          const int tiles_per_shape, const int num_tiles, const int stages)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
@@ -104,8 +72,9 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
 
-    // a tile is (shape b, tile index within the shape); the producer decides the walk, the consumers read
-    // each slot's tile from its plan
+    // tile walk shared by both roles: t = blockIdx.x + it * gridDim.x, kept as (shape b, tile in shape)
+    const int step_b = (int)gridDim.x / tiles_per_shape;
+    const int step_t = (int)gridDim.x - step_b * tiles_per_shape;
     int b = (int)blockIdx.x / tiles_per_shape;
     int tile = (int)blockIdx.x - b * tiles_per_shape;
     int s = 0;
@@ -126,7 +95,8 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     int nb = 0x7fffffff;
     if ((int)threadIdx.x >= NCONS) {
         pdl_wait();
-        if ((int)(threadIdx.x & 31) < V) nb = __ldg(bins + (int64_t)b * bin_sb + (threadIdx.x & 31));
+        if ((int)blockIdx.x < num_tiles && (int)(threadIdx.x & 31) < V)
+            nb = __ldg(bins + (int64_t)b * bin_sb + (threadIdx.x & 31));
     }
     __syncthreads();
     pdl_wait();
@@ -136,24 +106,15 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     if ((int)threadIdx.x >= NCONS) {
         // ------------------------------------------------------------------ producer warp
         const int lane = threadIdx.x & 31;
-        TileSlot *slot = &g_tile_slots[ticket % kTileSlots];
-        const bool dynamic = ticket != 0ull;
-        // t: this tile; t1: the next one (its bins are prefetched behind this tile's work); t2: the one
-        // after (its index is fetched from the counter behind this tile's work).  Indices only grow.
-        int t = blockIdx.x;
-        int t1 = (int)min((int64_t)blockIdx.x + (int64_t)gridDim.x, (int64_t)num_tiles);
-        if (dynamic && lane == 0) tile_slot_claim(slot, ticket);
-        while (t < num_tiles) {
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int64_t d0 = (int64_t)tile * TD;
             const uint32_t row_bytes = (uint32_t)min((int64_t)TD, D - d0) * sizeof(T);
             int bin = nb;
-            if (lane == 0 && t == (int)blockIdx.x && bin != 0x7fffffff) GVCNN_RING_MARK(5);
-            // next tile's coordinates and bins; the index of the one after
-            const int b_n = t1 / tiles_per_shape, tile_n = t1 - b_n * tiles_per_shape;
-            if (t1 < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b_n * bin_sb + lane);
-            // (the counter's answer is not needed before the bottom of the loop)
-            unsigned int got = 0;
-            if (dynamic && lane == 0 && t1 < num_tiles) got = atomicAdd(&slot->next, 1u);
+            if (lane == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(5);
+            // next tile's coordinates; prefetch its bins behind this tile's work
+            int b_n = b + step_b, tile_n = tile + step_t;
+            if (tile_n >= tiles_per_shape) { tile_n -= tiles_per_shape; ++b_n; }
+            if (t + (int)gridDim.x < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b_n * bin_sb + lane);
             if (lane < V && (bin < 0 || bin >= G)) {
                 if (status && tile == 0) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
                 bin = bin < 0 ? 0 : G - 1;
@@ -178,10 +139,8 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
             if (lane == 0) {
                 plans[s].first_mask = fm;
                 plans[s].tail_skip = (uint32_t)(G - 1 - last_bin);
-                plans[s].b = b;
-                plans[s].tile = tile;
             }
-            if (weights) {  // caller-supplied group weights (model.group_fusion's second argument; paper mode)
+            if constexpr (WTS) {  // caller-supplied group weights
                 const float *wrow = weights + (int64_t)b * w_sb;
                 if (lane < V) plans[s].gw[k] = __ldg(wrow + bin);
                 if (lane == 0) {
@@ -197,28 +156,11 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
                 bulk_g2s(smem_raw + (size_t)s * kStageBytes + (size_t)k * kRowStride,
                          fp.p[lane] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &full_bar[s]);
             if (lane == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(6);
-            int t2;
-            if (dynamic) {
-                got = __shfl_sync(0xffffffffu, got, 0);
-                const int64_t cand = 2 * (int64_t)gridDim.x + (int64_t)got;
-                t2 = (t1 < num_tiles && cand < (int64_t)num_tiles) ? (int)cand : num_tiles;
-            } else {
-                t2 = (int)min((int64_t)t1 + (int64_t)gridDim.x, (int64_t)num_tiles);
-            }
             b = b_n;
             tile = tile_n;
-            t = t1;
-            t1 = t2;
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        // end marker for the consumers, in the next slot of the ring
-        if (lane == 0) {
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            plans[s].b = -1;
-            mbar_arrive(&full_bar[s]);
-            if (dynamic) tile_slot_finish(slot, gridDim.x);
-            GVCNN_RING_MARK(3);
-        }
+        if (lane == 0) GVCNN_RING_MARK(3);
         return;
     }
 
@@ -226,48 +168,33 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     const int e0 = threadIdx.x * E;
     const float sumw = (float)(G + V);  // sum_g (1 + n_g): exact in float32 in any order
     const float rcp_sumw = __frcp_rn(sumw);
-    bool first_tile = true;
-    for (;;) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int64_t d0 = (int64_t)tile * TD;
+        const bool active = (int64_t)e0 < D - d0;
+        const int64_t out_off = (int64_t)b * D + d0 + e0;
         const unsigned char *col = smem_raw + (size_t)s * kStageBytes + (size_t)threadIdx.x * 16;
 
         mbar_wait(&full_bar[s], ph);
-        if (threadIdx.x == 0 && first_tile) GVCNN_RING_MARK(1);
-        first_tile = false;
-        b = plans[s].b;  // which tile the producer put here
-        if (b < 0) break;
-        const int64_t d0 = (int64_t)plans[s].tile * TD;
-        const bool active = (int64_t)e0 < D - d0;
-        const int64_t out_off = (int64_t)b * D + d0 + e0;
+        if (threadIdx.x == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(1);
 
         float acc[E];
-        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc,
-                                                        weights != nullptr);
-        const float sw_given = weights ? plans[s].sumw : 0.0f;
+        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc, WTS);
+        const float sw_given = WTS ? plans[s].sumw : 0.0f;
         // every lane of the warp is done reading the slot: hand it back to the producer
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
         if (active) {
 #pragma unroll
             for (int e = 0; e < E; ++e)
-                acc[e] = weights ? __fdiv_rn(acc[e], sw_given) : div_by_rcp(acc[e], sumw, rcp_sumw);
+                acc[e] = WTS ? __fdiv_rn(acc[e], sw_given) : div_by_rcp(acc[e], sumw, rcp_sumw);
             stg_stream_16(S + out_off, Elem<T>::pack(acc));
         }
+        b += step_b;
+        tile += step_t;
+        if (tile >= tiles_per_shape) { tile -= tiles_per_shape; ++b; }
         if (++s == stages) { s = 0; ph ^= 1u; }
     }
     if (threadIdx.x == 0) GVCNN_RING_MARK(2);
-}
-
-// process-wide launch ticket (see TileSlot); GVCNN_RING_DYNAMIC=0 selects the static walk for A/B runs
-static unsigned long long ring_next_ticket()
-{
-    static std::atomic<unsigned long long> next{1};
-    static const bool dynamic = [] {
-        const char *env = getenv("GVCNN_RING_DYNAMIC");
-        return !(env && env[0] == '0');
-    }();
-    if (!dynamic) return 0ull;
-    unsigned long long t = next.fetch_add(1, std::memory_order_relaxed);
-    return t ? t : next.fetch_add(1, std::memory_order_relaxed);
 }
 
 static int ring_sm_count()
@@ -308,22 +235,26 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
     const int64_t max_grid = (int64_t)ring_sm_count() * MINB;
     const int grid = (int)(tiles < max_grid ? tiles : max_grid);
     const bool want_mask = (mask != nullptr) && pool == GVCNN_POOL_MAX;
-    // short walks (a handful of rounds) gain nothing from the counter and pay its latency: static
-    const unsigned long long ticket = tiles >= 6 * (int64_t)grid ? ring_next_ticket() : 0ull;
     cudaError_t err = cudaSuccess;
-#define GVCNN_LAUNCH_RING(POOL_, MASK_)                                                                      \
+#define GVCNN_LAUNCH_RING(POOL_, MASK_, WTS_)                                                                \
     do {                                                                                                     \
-        auto kern = pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, V, NCONS, MINB>;                              \
+        auto kern = pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, WTS_, V, NCONS, MINB>;                        \
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (err == cudaSuccess)                                                                              \
             err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
                              bin_sb, weights, w_sb, static_cast<T *>(S), mask, status, B, D, G, fill,        \
-                             (int)tps, (int)tiles, stages, ticket);                                          \
+                             (int)tps, (int)tiles, stages);                                                  \
     } while (0)
-    if (pool == GVCNN_POOL_MAX) {
-        if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false);
+    if (weights) {
+        if (pool == GVCNN_POOL_MAX) {
+            if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true, true); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false, true);
+        } else {
+            GVCNN_LAUNCH_RING(GVCNN_POOL_MEAN, false, true);
+        }
+    } else if (pool == GVCNN_POOL_MAX) {
+        if (want_mask) GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, true, false); else GVCNN_LAUNCH_RING(GVCNN_POOL_MAX, false, false);
     } else {
-        GVCNN_LAUNCH_RING(GVCNN_POOL_MEAN, false);
+        GVCNN_LAUNCH_RING(GVCNN_POOL_MEAN, false, false);
     }
 #undef GVCNN_LAUNCH_RING
     if (err != cudaSuccess) return (int)err;

@@ -12,8 +12,7 @@ constexpr int kRingProducerThreads = 32;
 struct __align__(16) RingPlan {
     uint32_t first_mask;  // bit k: the k-th sorted view starts a group
     uint32_t tail_skip;   // empty groups after the last non-empty one
-    int32_t b;            // shape of the tile in this slot; -1 = no more tiles (pool_fwd_ring.cu, dynamic walk)
-    int32_t tile;         // tile index within the shape
+    uint32_t pad[2];
     uint8_t skip[32];     // at a group start k: empty groups between the previous group and this one
     float gw[32];         // caller-supplied weights only: weight of the group sorted view k is in
     float sumw;           // caller-supplied weights only: sum of all G weights (left to right)
@@ -153,11 +152,9 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                         }
                     }
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);  // acc += w_g * P_g
+                    if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, cnt);
 #pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        if (POOL == GVCNN_POOL_MEAN) m[e] = __fdiv_rn(m[e], (float)cnt);
-                        acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
-                    }
+                    for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
                 }
                 if (fill != 0.0f) {  // empty groups in between / after: w = 1, P = fill
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);

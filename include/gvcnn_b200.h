@@ -9,12 +9,8 @@
  *
  * Conventions (all entry points):
  *   - every tensor pointer is a DEVICE pointer owned by the caller unless the
- *     name says `host`; the library allocates nothing and keeps no state that
- *     outlives a call apart from gvcnn_set_pool_variant's selector and a
- *     64-entry scheduling scratch in device globals (the pooling kernel's
- *     per-launch tile counters, claimed and zeroed again by the launch that
- *     uses them); calls are stream-ordered, asynchronous and re-entrant
- *     across streams and host threads;
+ *     name says `host`; the library allocates nothing persistent and keeps no
+ *     global state; calls are stream-ordered, asynchronous and re-entrant;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - return value: 0 = ok, < 0 = GVCNN_E_* argument error (nothing was
  *     launched), > 0 = a cudaError_t from the launch;  nothing throws;

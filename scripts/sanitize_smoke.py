@@ -22,7 +22,7 @@ cases = [  # B, V, D, G, dtype, pool
     (3, 40, 2048, 3, torch.bfloat16, "max"),   # chunked bf16
     (4, 5, 100, 5, torch.float32, "max"),      # generic one-shot (V not templated), small D
     (2, 12, 7, 8, torch.float32, "mean"),      # scalar fallback (unaligned D)
-    (900, 4, 2048, 4, torch.float32, "max"),   # ring, 1800 tiles: dynamic tile hand-out (counter slot)
+    (900, 4, 2048, 4, torch.float32, "max"),   # ring, 1800 tiles: ~6 per CTA, ring slots re-used
 ]
 for B, V, D, G, dt, pool in cases:
     F = torch.relu(torch.randn(B, V, D, device=dev)).to(dt).requires_grad_(True)

@@ -597,7 +597,7 @@ def test_streams_are_independent(model):
 @pytest.mark.parametrize("V", [6, 12, 20])
 def test_long_walks_every_ring_variant(model, c_oracle, V, pool, fill, dtype):
     """B = 2048 gives every instantiation of the ring kernel (two CTAs per SM at V <= 12, one at V = 20; packed
-    bf16; tie mask; mean) a walk of >= 6 rounds, i.e. the dynamic tile hand-out with re-used ring slots:
+    bf16; tie mask; mean) a walk of many rounds, i.e. every ring slot is re-used several times:
     forward, tie mask -> backward, bit-exact against the C oracle."""
     B, D, G = 2048, 2048, 8
     F, bins, dS = make_inputs(V * 7 + (dtype == "bf16"), B, V, D, G, ties=True)
@@ -618,12 +618,11 @@ def test_long_walks_every_ring_variant(model, c_oracle, V, pool, fill, dtype):
 
 
 @pytest.mark.timeout(300)
-def test_dynamic_tile_handout_with_colliding_launches(model):
-    """Long tile walks draw their tiles from a per-launch counter slot (pool_fwd_ring.cu, TileSlot; slot =
-    launch ticket % 64).  Queue 64 launches on each of two streams behind a spin kernel so that launch k of
-    stream A and launch k of stream B (tickets 64 apart: the same slot) contend for SMs at the same time, with
-    different inputs, masks on one side only; every result must still be the oracle's, bit for bit."""
-    B, V, D, G = 1024, 12, 2048, 8                       # 2048 tiles >= 6 rounds of 296 CTAs: dynamic walk
+def test_two_streams_contending_for_the_sms(model):
+    """Persistent kernels from two streams compete for the same SM slots: queue 64 launches on each stream
+    behind a spin kernel so both queues are full before anything runs, with different inputs and the tie-mask
+    variant on one side only; every result must still be the oracle's, bit for bit."""
+    B, V, D, G = 1024, 12, 2048, 8                       # 2048 tiles: ~7 per CTA, ring slots are re-used
     F1, b1, _ = make_inputs(11, B, V, D, G)
     F2, b2, _ = make_inputs(12, B, V, D, G, ties=True)
     x1, x2, bb1, bb2 = dev(F1), dev(F2), dev(b1), dev(b2)
@@ -676,6 +675,30 @@ def test_sweep_grid_parity(model, c_oracle, V, G, D, pool, fill, dtype):
         want, wantg = O.round_bf16(want), O.round_bf16(wantg)
     np.testing.assert_array_equal(S.detach().float().cpu().numpy(), want)
     np.testing.assert_array_equal(x.grad.float().cpu().numpy(), wantg)
+
+
+@pytest.mark.parametrize("V,D", [(12, 2048), (16, 1024), (5, 100), (40, 1024)])
+def test_mean_division_shortcuts_are_exact(model, V, D):
+    """mean_of_sum (csrc/common.cuh) skips the division for singleton groups and multiplies by 2^-k for
+    power-of-two group sizes; both must equal the float32 division for every value class: subnormal sums and
+    quotients, the largest finite values, infinities produced by the sum, signed zeros.  Group sizes 1..V all
+    occur (shape i puts its first i+1 views in one group); ring, generic and chunked kernels."""
+    G = V
+    B = 2 * V
+    rng = np.random.default_rng(V)
+    mag = np.array([1e-45, 1e-41, 1.2e-38, 3e-38, 1e-30, 1.0, 3.0, 1e30, 1.7e38, 3.4e38], dtype=np.float32)
+    F = (rng.choice(mag, (B, V, D)) * rng.choice(np.array([-1, 1], np.float32), (B, V, D))).astype(np.float32)
+    F[:, :, :8] = 0.0
+    F[:, ::2, :4] = -0.0
+    bins = np.zeros((B, V), dtype=np.int32)
+    for i in range(B):
+        n = i % V + 1                       # the first n views share group 0, the others get their own
+        bins[i, n:] = np.arange(1, V - n + 1)
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = O.pool_fuse_fwd(F, bins, G, "mean", 0.0)
+    got = model.pool_fuse(dev(F), dev(bins), G, pool="mean", empty_fill=0.0).cpu().numpy()
+    np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
 
 
 def test_cuda_graph_capture_and_replay(model):
