@@ -24,7 +24,7 @@ struct __align__(16) BwdPlan {
 
 // GAP: dS is the gradient of the global average pool that follows the fusion, [B, C] (D = HW * C,
 // channel-last): dS[b, p, c] = dOut[b, c] / HW (tf.reduce_mean's gradient), never materialised.
-template <typename T, int POOL, int V, int NT, bool GAP>
+template <typename T, int POOL, int V, int NT, bool GAP, bool WTS>
 __global__ void __launch_bounds__(NT)
 pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins, const int64_t bin_sb,
                           const uint8_t *__restrict__ mask, const float *__restrict__ weights, const int64_t w_sb,
@@ -99,11 +99,11 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             const int start = k - same_before;
             plan.seg[k] = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << start;
             plan.rowptr[k] = (unsigned long long)(gp.p[lane] + ((int64_t)b * g_sb + d0) * (int64_t)sizeof(T));
-            if (weights) plan.gw[k] = __ldg(weights + (int64_t)b * w_sb + bin);
+            if constexpr (WTS) plan.gw[k] = __ldg(weights + (int64_t)b * w_sb + bin);
         }
         if (lane == 0) {
             plan.first_mask = fm;
-            if (weights) {
+            if constexpr (WTS) {
                 float sw = 0.0f;
                 for (int g = 0; g < G; ++g) sw = __fadd_rn(sw, __ldg(weights + (int64_t)b * w_sb + g));
                 plan.sumw = sw;
@@ -113,7 +113,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
     __syncthreads();
     if (!active) return;
 
-    const bool wts = weights != nullptr;
+    constexpr bool wts = WTS;  // caller-supplied group weights: compiled out of the default instantiation
     const float sumw = wts ? plan.sumw : (float)(G + V);
     const float rcp_sumw = __frcp_rn((float)(G + V));
     float t[E];
@@ -220,15 +220,24 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
     if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
     const unsigned grid = (unsigned)(B * tiles);
     cudaError_t err;
-#define GVCNN_LAUNCH_BF(POOL_, GAP_)                                                                          \
-    err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_>, dim3(grid), dim3(NT), 0, st,           \
+#define GVCNN_LAUNCH_BF(POOL_, GAP_, WTS_)                                                                    \
+    err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_, WTS_>, dim3(grid), dim3(NT), 0, st,     \
                      static_cast<const T *>(dS), bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G,   \
                      (int)tiles, gapC, gapHW)
+#define GVCNN_LAUNCH_BF_P(GAP_, WTS_)                                                                         \
+    do {                                                                                                      \
+        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, GAP_, WTS_);                              \
+        else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, GAP_, WTS_);                                                    \
+    } while (0)
     if (gapC > 0) {
-        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, true);
+        if (weights) return GVCNN_E_UNSUPPORTED;  // the GAP-folded backward always uses the reference's weights
+        GVCNN_LAUNCH_BF_P(true, false);
+    } else if (weights) {
+        GVCNN_LAUNCH_BF_P(false, true);
     } else {
-        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, false); else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, false);
+        GVCNN_LAUNCH_BF_P(false, false);
     }
+#undef GVCNN_LAUNCH_BF_P
 #undef GVCNN_LAUNCH_BF
     if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
