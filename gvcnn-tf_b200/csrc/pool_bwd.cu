@@ -130,8 +130,7 @@ __global__ void pool_fuse_bwd_kernel(const T *__restrict__ dS, const int32_t *__
                 else *reinterpret_cast<T *>(dst) = Elem<T>::from_float(o[0]);
             }
         } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) val[e] = __fdiv_rn(val[e], (float)len);
+            mean_of_sum(val, (int)len);  // g / n with the division left out for n = 1, 2, 4, ...
             uint4 packed;
             if constexpr (VEC) packed = Elem<T>::pack(val);
             for (int j = 0; j < len; ++j) {

@@ -185,14 +185,22 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
                 const uint32_t seg = plan.seg[k];
                 const int n = __popc(seg);
                 const float w = wts ? plan.gw[k] : (float)(1 + n);
+                // mean: g1 / n.  n is uniform; for n a power of two 1/n is exact and the product is the
+                // correctly rounded quotient (n == 1 included), otherwise the exact division by reciprocal
+                if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const float g1 = __fmul_rn(t[e], w);
-                    if constexpr (POOL == GVCNN_POOL_MAX) {
+                    for (int e = 0; e < E; ++e) {
                         const int nsel = __popc(me[e] & seg);
-                        val[e] = __fmul_rn(rcp_tab[nsel], g1);  // (1 / num_selected) * g1; nsel == 0 only for NaN
+                        val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));  // (1 / num_selected) * g1; nsel == 0 only for NaN
+                    }
+                } else {
+                    const float rn = rcp_tab[n];
+                    if ((n & (n - 1)) == 0) {  // uniform branch
+#pragma unroll
+                        for (int e = 0; e < E; ++e) val[e] = __fmul_rn(__fmul_rn(t[e], w), rn);
                     } else {
-                        val[e] = div_by_rcp(g1, (float)n, rcp_tab[n]);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) val[e] = div_by_rcp(__fmul_rn(t[e], w), (float)n, rn);
                     }
                 }
                 if constexpr (POOL == GVCNN_POOL_MEAN) packed = Elem<T>::pack(val);

@@ -696,9 +696,20 @@ def test_mean_division_shortcuts_are_exact(model, V, D):
         bins[i, n:] = np.arange(1, V - n + 1)
     with np.errstate(over="ignore", invalid="ignore"):
         want = O.pool_fuse_fwd(F, bins, G, "mean", 0.0)
-    got = model.pool_fuse(dev(F), dev(bins), G, pool="mean", empty_fill=0.0).cpu().numpy()
+    x = dev(F).requires_grad_(True)
+    S = model.pool_fuse(x, dev(bins), G, pool="mean", empty_fill=0.0)
+    got = S.detach().cpu().numpy()
     np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
     assert np.array_equal(np.isnan(got), np.isnan(want))
+    # the same shortcuts in the backward (g / n): gradients of every magnitude class
+    dS = (rng.choice(mag, (B, D)) * rng.choice(np.array([-1, 1], np.float32), (B, D))).astype(np.float32)
+    S.backward(dev(dS))
+    with np.errstate(over="ignore", invalid="ignore"):
+        wantg = O.pool_fuse_bwd(dS, F, bins, G, "mean")
+    gotg = x.grad.cpu().numpy()
+    ok = ~np.isnan(wantg)
+    np.testing.assert_array_equal(gotg.view(np.uint32)[ok], wantg.view(np.uint32)[ok])
+    assert np.array_equal(np.isnan(gotg), np.isnan(wantg))
 
 
 def test_cuda_graph_capture_and_replay(model):
