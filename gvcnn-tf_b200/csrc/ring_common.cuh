@@ -76,17 +76,17 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             if (k == V || k == 0 || ((fm >> k) & 1u)) {
                 if (k > 0) {
                     if constexpr (MASK) {
+                        // tie bit of the group's last member now; then park the group max in its (no longer
+                        // needed) registers for the backward sweep below, which does the other members
+                        const int kl = k > 0 ? k - 1 : 0;  // compile-time after unrolling
+                        const uint32_t xw[4] = {raw[kl].x, raw[kl].y, raw[kl].z, raw[kl].w};
 #pragma unroll
-                        for (int j = 1; j <= k; ++j) {
-                            if (j > cnt) break;
-                            const uint32_t xw[4] = {raw[k - j].x, raw[k - j].y, raw[k - j].z, raw[k - j].w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint32_t eq = bf16x2_eq_mask(xw[i], m2[i]);
-                                if (k - j < 16) me2[i] |= eq & (0x00010001u << ((k - j) & 15));
-                                else me2b[i] |= eq & (0x00010001u << ((k - j) & 15));
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t eq = bf16x2_eq_mask(xw[i], m2[i]);
+                            if (kl < 16) me2[i] |= eq & (0x00010001u << (kl & 15));
+                            else me2b[i] |= eq & (0x00010001u << (kl & 15));
                         }
+                        raw[kl] = make_uint4(m2[0], m2[1], m2[2], m2[3]);
                     }
                     float m[E];
                     Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
@@ -114,6 +114,24 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             }
         }
         if constexpr (MASK) {
+            // backward sweep: every view that is not the last of its group is compared with the group max
+            // parked at the group's last position (O(V) code; the walk above closes groups at static k)
+            uint32_t cm[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = V - 1; k >= 0; --k) {
+                const bool last = (k == V - 1) || (((fm >> (k + 1 < 32 ? k + 1 : 31)) & 1u) != 0u);
+                if (last) {
+                    cm[0] = raw[k].x; cm[1] = raw[k].y; cm[2] = raw[k].z; cm[3] = raw[k].w;
+                } else {
+                    const uint32_t xw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t eq = bf16x2_eq_mask(xw[i], cm[i]);
+                        if (k < 16) me2[i] |= eq & (0x00010001u << (k & 15));
+                        else me2b[i] |= eq & (0x00010001u << (k & 15));
+                    }
+                }
+            }
             // byte planes: plane p, element e -> bits 8(p&1).. of the half of me2/me2b[e >> 1]
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -140,16 +158,15 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             if (k == V || k == 0 || ((fm >> k) & 1u)) {  // uniform: a group ends / starts here
                 if (k > 0) {                             // close the previous group
                     if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
-                        // its members are the cnt rows before k: compare each with the group max
+                        // tie bit of the group's last member now; then park the group max in its (no longer
+                        // needed) registers for the backward sweep below, which does the other members
+                        const int kl = k > 0 ? k - 1 : 0;  // compile-time after unrolling
+                        float x[E];
+                        Elem<T>::unpack(raw[kl], x);
 #pragma unroll
-                        for (int j = 1; j <= k; ++j) {
-                            if (j > cnt) break;
-                            float x[E];
-                            Elem<T>::unpack(raw[k - j], x);
-#pragma unroll
-                            for (int e = 0; e < E; ++e)
-                                if (x[e] == m[e]) me[e] |= 1u << (k - j);
-                        }
+                        for (int e = 0; e < E; ++e)
+                            if (x[e] == m[e]) me[e] |= 1u << kl;
+                        raw[kl] = Elem<T>::pack(m);  // exact: m is a max of values of type T
                     }
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);  // acc += w_g * P_g
                     if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, cnt);
@@ -178,6 +195,24 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             }
         }
         if constexpr (MASK && POOL == GVCNN_POOL_MAX) {
+            // backward sweep: every view that is not the last of its group is compared with the group max
+            // parked at the group's last position (O(V) code; the walk above closes groups at static k)
+            float cm[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) cm[e] = 0.0f;
+#pragma unroll
+            for (int k = V - 1; k >= 0; --k) {
+                const bool last = (k == V - 1) || (((fm >> (k + 1 < 32 ? k + 1 : 31)) & 1u) != 0u);
+                if (last) {
+                    Elem<T>::unpack(raw[k], cm);
+                } else {
+                    float x[E];
+                    Elem<T>::unpack(raw[k], x);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (x[e] == cm[e]) me[e] |= 1u << k;
+                }
+            }
             // transpose to byte planes: byte e of plane word p = bits 8p..8p+7 of me[e]
 #pragma unroll
             for (int p = 0; p < P; ++p) {
