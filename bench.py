@@ -524,12 +524,13 @@ def run_cuda_arm(args):
     line["roofline"].update(line.pop("_roofline_rest"))
     if world == 1 and not args.no_cpu_baseline:
         Bc = B                                                       # the full configs[1] batch
-        times, threads = cpu_reference_time(Bc, 8, 1)
+        times, threads = cpu_reference_time(Bc, 48, 2)               # ~10-15 s of CPU work
         best = min(times)
         line["cpu_baseline"] = {"value": Bc / best, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "best of 8 forward passes over the full %d-shape batch (%.0f ms each, %.1f s of "
+                                "mean_value": Bc * len(times) / sum(times),
+                                "sample": "best of %d forward passes over the full %d-shape batch (%.0f ms best, %.1f s of "
                                           "CPU work): the reference's op graph (nets/model.py:16-102) restated in "
-                                          "torch-CPU, all host threads" % (Bc, best * 1e3, sum(times))}
+                                          "torch-CPU, all host threads" % (len(times), Bc, best * 1e3, sum(times))}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

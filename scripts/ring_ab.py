@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B timing of the pooling forward for a few (V, D, dtype, pool) points (B=4096, G=8): CUDA-event time of 60 back-to-back
-launches / 60 (best of 3), rotating inputs.  Used with GVCNN_RING_DYNAMIC=0/1 to compare the static and the dynamic tile walk."""
+launches / 60 (best of 3), rotating inputs.  GVCNN_LIB=<path> times an older build of the library on the same box (bisecting regressions)."""
 import ctypes, os, statistics, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
