@@ -267,15 +267,19 @@ static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
                          cudaStream_t st)
 {
     // the view counts of the reference's configurations (train.py:96 default 6; BASELINE sweep 6/12/20)
-    // plus the other common multi-view rigs (4, 8, 16)
+    // plus the other common multi-view rigs (4, 8, 16).  V <= 12: 256-column tiles, two CTAs per SM, 4 slots
+    // each.  V = 16 / 20: a 256-column slot is 64 / 80 KB and only two fit per SM, so tiles are 128 columns
+    // wide and two CTAs share the SM with two slots each - four independent slots drain and refill more
+    // smoothly than two (V = 20: forward 111.7 -> 109.5 us, with tie mask 130.3 -> 126.1 us); for V <= 12 the
+    // narrow tiles (four CTAs per SM) measured the same as the wide ones.
     if (D < 256 * Elem<T>::kVec) return -1000;  // tiles narrower than one consumer row: generic kernel
     switch (V) {
     case 4: return launch_ring_v<T, 4, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
     case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
     case 8: return launch_ring_v<T, 8, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);  // GVCNN paper: 8 / 12 views
     case 12: return launch_ring_v<T, 12, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 16: return launch_ring_v<T, 16, 256, 1>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
-    case 20: return launch_ring_v<T, 20, 256, 1>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 16: return launch_ring_v<T, 16, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+    case 20: return launch_ring_v<T, 20, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
     default: return -1000;
     }
 }

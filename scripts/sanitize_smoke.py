@@ -17,7 +17,7 @@ cases = [  # B, V, D, G, dtype, pool
     (7, 12, 2048, 8, torch.float32, "max"),    # ring + bwd_fast
     (5, 12, 3076, 8, torch.float32, "max"),    # ring, partial last tile
     (5, 6, 1024, 10, torch.bfloat16, "max"),   # packed bf16
-    (4, 20, 2048, 16, torch.float32, "mean"),  # V = 20, one CTA per SM variant
+    (4, 20, 2048, 16, torch.float32, "mean"),  # V = 20: 128-column tiles, two CTAs per SM
     (3, 80, 1032, 4, torch.float32, "max"),    # chunked + plane fix-up, generic bwd
     (3, 40, 2048, 3, torch.bfloat16, "max"),   # chunked bf16
     (4, 5, 100, 5, torch.float32, "max"),      # generic one-shot (V not templated), small D

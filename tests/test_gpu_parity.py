@@ -596,7 +596,7 @@ def test_streams_are_independent(model):
 @pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
 @pytest.mark.parametrize("V", [6, 12, 20])
 def test_long_walks_every_ring_variant(model, c_oracle, V, pool, fill, dtype):
-    """B = 2048 gives every instantiation of the ring kernel (two CTAs per SM at V <= 12, one at V = 20; packed
+    """B = 2048 gives every instantiation of the ring kernel (wide tiles at V <= 12, narrow ones at V = 20; packed
     bf16; tie mask; mean) a walk of many rounds, i.e. every ring slot is re-used several times:
     forward, tie mask -> backward, bit-exact against the C oracle."""
     B, D, G = 2048, 2048, 8
