@@ -20,7 +20,7 @@
 // takes the generic kernel in pool_fwd.cu.
 //
 // The tile walk is static (t = blockIdx.x, blockIdx.x + gridDim.x, ...).  A dynamic hand-out from a per-launch
-// counter was built and measured (DESIGN.md 3.7): it shortens the spread of CTA end times (median idle 3 -> 1.2 us
+// counter was built and measured (DESIGN.md 3.2): it shortens the spread of CTA end times (median idle 3 -> 1.2 us
 // in scripts/ring_trace_probe.cu) but is neutral to slower once launches run back to back, and slower for small
 // tiles (V = 6) and shallow rings (V = 20) because the compiler emits the one-lane atomic in its warp-aggregated
 // form, which waits for the counter on the spot.
