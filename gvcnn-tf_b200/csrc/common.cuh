@@ -104,12 +104,15 @@ __device__ __forceinline__ void build_plan(Plan &pl, const int32_t *__restrict__
 }
 
 // ---- memory helpers --------------------------------------------------------
+// read-once data: not kept in L1, and allocated evict-first in L2 (see l2_policy_evict_first below)
 __device__ __forceinline__ uint4 ldg_stream_16(const void *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));  // not volatile: hoisted / shared
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void stg_stream_16(void *p, const uint4 &v)
@@ -163,6 +166,25 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             smem_u32(smem_dst)),
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Same copy with an L2 eviction-priority hint: the rows are read exactly once, so they are allocated evict-first
+// and replace each other in L2 instead of pushing out (and forcing the write-back of) whatever the previous
+// kernel left there.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 

@@ -56,7 +56,7 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
                           const int64_t bin_sb, const float *__restrict__ weights, const int64_t w_sb,
                           T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
                           const int B, const int64_t D, const int G, const float fill,
-                          const int tiles_per_shape, const int num_tiles, const int stages)
+                          const int tiles_per_shape, const int num_tiles, const int stages, const int l2_hint)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
@@ -106,6 +106,7 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     if ((int)threadIdx.x >= NCONS) {
         // ------------------------------------------------------------------ producer warp
         const int lane = threadIdx.x & 31;
+        const uint64_t policy = l2_policy_evict_first();
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int64_t d0 = (int64_t)tile * TD;
             const uint32_t row_bytes = (uint32_t)min((int64_t)TD, D - d0) * sizeof(T);
@@ -152,9 +153,14 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full_bar[s], row_bytes * (uint32_t)V);
             __syncwarp();
-            if (lane < V)
-                bulk_g2s(smem_raw + (size_t)s * kStageBytes + (size_t)k * kRowStride,
-                         fp.p[lane] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &full_bar[s]);
+            if (lane < V) {
+                if (l2_hint)
+                    bulk_g2s_hint(smem_raw + (size_t)s * kStageBytes + (size_t)k * kRowStride,
+                                  fp.p[lane] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &full_bar[s], policy);
+                else
+                    bulk_g2s(smem_raw + (size_t)s * kStageBytes + (size_t)k * kRowStride,
+                             fp.p[lane] + ((int64_t)b * f_sb + d0) * (int64_t)sizeof(T), row_bytes, &full_bar[s]);
+            }
             if (lane == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(6);
             b = b_n;
             tile = tile_n;
@@ -227,6 +233,8 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
         if (want >= 2 && want <= stages) stages = want;
     }
     if (stages < 2) return -1000;
+    int l2_hint = 1;
+    if (const char *env = getenv("GVCNN_RING_L2HINT")) l2_hint = atoi(env);  // tuning knob for A/B runs
     const int64_t td = (int64_t)NCONS * E;
     const int64_t tps = (D + td - 1) / td;
     const int64_t tiles = (int64_t)B * tps;
@@ -243,7 +251,7 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
         if (err == cudaSuccess)                                                                              \
             err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
                              bin_sb, weights, w_sb, static_cast<T *>(S), mask, status, B, D, G, fill,        \
-                             (int)tps, (int)tiles, stages);                                                  \
+                             (int)tps, (int)tiles, stages, l2_hint);                                         \
     } while (0)
     if (weights) {
         if (pool == GVCNN_POOL_MAX) {
