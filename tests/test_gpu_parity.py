@@ -571,6 +571,35 @@ def test_real_geometry_spatial_maps(model, c_oracle):
     np.testing.assert_array_equal(got, wantg)
 
 
+def test_config0_eval_path_inception_geometry(model, c_oracle):
+    """BASELINE.json configs[0] restated: the reference's eval step (eval.py:177-202) on a
+    synthetic 6-view batch of 8 shapes with the Inception-v3 head geometry - final maps [8, 8, 8, 2048] per view
+    (Mixed_7c, nets/inception_v3.py:386), NUM_GROUP = 10 - through the reference-named calls: view_scores
+    (batch mean) -> group_scheme -> group_weight -> view_pooling -> group_fusion -> GAP.  The backbone itself is
+    out of scope; its outputs are synthetic."""
+    N, V, G, Cr = 8, 6, 10, 1024
+    rng = np.random.default_rng(40)
+    F = np.maximum(rng.standard_normal((V, N, 8, 8, 2048)), 0).astype(np.float32)       # post-ReLU maps
+    R, W, b = score_inputs(41, N, V, Cr, bias_range=3.0)
+    scores = model.view_scores(dev(R), dev(W), dev(b))                                  # [1, V]
+    x64 = c_oracle.view_score_x_f64(R, W, b).mean(axis=0)
+    s64 = O.score_from_x(x64)
+    np.testing.assert_allclose(scores.cpu().numpy()[0], s64, rtol=0, atol=2e-5)
+    scheme = model.group_scheme([scores[0]], G, V)                                       # [G, V] one-hot
+    got_bins = scheme.cpu().numpy().argmax(axis=0).astype(np.int32)
+    near = np.abs(s64 * G - np.round(s64 * G)) < 1e-4
+    assert ((got_bins == np.trunc(s64 * G).astype(np.int32)) | near).all()
+    weight = model.group_weight(scheme)
+    np.testing.assert_array_equal(weight.cpu().numpy(), O.group_weight(scheme.cpu().numpy()))
+    S = model.group_fusion(model.view_pooling([dev(F[v]) for v in range(V)], scheme), weight)
+    assert tuple(S.shape) == (N, 8, 8, 2048)
+    want = c_oracle.pool_fuse_fwd(F.reshape(V, N, -1), got_bins, G, "max", 1.0, layout="vbd")
+    np.testing.assert_array_equal(S.cpu().numpy().reshape(N, -1), want)
+    # the descriptor the classifier sees (GlobalAveragePooling2D, nets/model.py:163), folded and unfolded
+    gap = model.pool_fuse_gap([dev(F[v]) for v in range(V)], dev(np.tile(got_bins, (N, 1))), G)
+    np.testing.assert_allclose(gap.cpu().numpy(), want.reshape(N, 64, 2048).mean(axis=1), rtol=1e-5, atol=1e-6)
+
+
 def test_streams_are_independent(model):
     """The C ABI is stream-ordered and re-entrant: two streams, different problems, interleaved calls."""
     F1, b1, _ = make_inputs(1, 300, 12, 2048, 8)
