@@ -47,3 +47,27 @@ def test_algorithmic_bytes_match_baseline_md():
     assert ab["bwd"] == 106496 and ab["fwd_bwd"] == 262240
     ab2 = bench.algorithmic_bytes(1, 12, 2048, 1024, 2)
     assert ab2["fwd"] == 77920 and ab2["fwd_bwd"] == 131168
+
+
+def test_committed_cuda_arm_line_has_the_contract_keys():
+    """The CUDA arm cannot run here; the line it printed on the B200 box (profiles/r01z_bench_n1.json) is checked
+    against the contract instead, so a change of bench.py's keys without a re-measurement is caught."""
+    with open(os.path.join(ROOT, "profiles", "r01z_bench_n1.json")) as f:
+        line = json.load(f)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["unit"] == "shapes/s" and line["dtype"] == "f32" and line["vs_baseline"] is None
+    assert line["gpu_launches"] == 2 * line["steps"] and "workload" in line["config"] and "l2" in line["config"]
+    r = line["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0.9 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.1      # no wasted re-reads
+    c = line["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] == 4096 * 12 * (1024 + 2048) * 4 and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < line["value"]                                     # host copies are inside the e2e region
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
