@@ -244,3 +244,25 @@ def test_reference_gvcnn_head_end_to_end(golden_dir, case):
     basic = z["%s__basic_descriptor" % case]
     one = O.group_fusion(O.view_pooling([g["F"][v] for v in range(V)], np.ones((1, V), dtype=np.int64)), np.ones(1))
     np.testing.assert_array_equal(one, basic)
+
+
+def test_power_of_two_mean_shortcut_is_exact_in_float32():
+    """The kernels' group mean multiplies by 2^-k instead of dividing when the group size is 2^k
+    (csrc/common.cuh mean_of_sum; the backward's reciprocal table): both are the correctly rounded value of the
+    same real number, for every float32 - normal, subnormal (also when only the quotient is subnormal), zero,
+    infinite.  Checked here on the host for 4 million random bit patterns plus the boundary values per k."""
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2 ** 32, 4_000_000, dtype=np.uint64).astype(np.uint32)
+    edge = np.array([0x00000000, 0x80000000, 0x00000001, 0x00000002, 0x00000003, 0x007fffff, 0x00800000, 0x00800001,
+                     0x00ffffff, 0x01000000, 0x7f7fffff, 0x7f800000, 0xff800000, 0x3f800000, 0x3fffffff],
+                    dtype=np.uint32)
+    x = np.concatenate([bits, edge]).view(np.float32)
+    ok = ~np.isnan(x)
+    x = x[ok]
+    with np.errstate(under="ignore", over="ignore"):
+        for k in range(1, 6):                                       # group sizes 2, 4, 8, 16, 32
+            n = np.float32(2 ** k)
+            r = np.float32(1.0) / n
+            assert r * n == 1.0                                     # the reciprocal is exact
+            a, b = (x * r).view(np.uint32), (x / n).view(np.uint32)
+            assert np.array_equal(a, b), k
