@@ -15,11 +15,21 @@ SO_PATH = os.path.join(_HERE, "libgvcnn_sm100.so")
 F32, BF16 = 0, 1
 LAYOUT_BVD, LAYOUT_VBD, LAYOUT_PTRS = 0, 1, 2
 POOL_MAX, POOL_MEAN = 0, 1
+SCORE_REDUCE_SHAPE, SCORE_REDUCE_BATCH = 0, 1
+ABI_VERSION = 2
+EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
+
+
+def pool_variant(pool, variant=0):
+    """GVCNN_POOL_VARIANT: A/B-test selection of the pooling kernel, carried in bits 8..11 of `pool`."""
+    return pool | (variant << 8)
 STATUS_WORDS = 4
 STATUS_BIN_RANGE, STATUS_NAN, STATUS_NEAR_EDGE, STATUS_BAD_SCHEME = 0, 1, 2, 3
 FLAG_NEAR_EDGE, FLAG_BIN_RANGE, FLAG_NAN = 1, 2, 4
 MAX_VIEWS, MAX_GROUPS = 128, 4096
 E_UNSUPPORTED = -10
+E_COMM_TIMEOUT = -11
+COMM_MAX_WORLD, COMM_MAX_FLOATS, COMM_HANDLE_BYTES = 8, 16384, 64
 
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 
@@ -28,12 +38,11 @@ SIGNATURES = {
     "gvcnn_version": (_i, []),
     "gvcnn_strerror": (ctypes.c_char_p, [_i]),
     "gvcnn_check_device": (_i, []),
-    "gvcnn_set_pool_variant": (_i, [_i]),
     "gvcnn_view_score_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_batch_sum_x": (_i, [_vp, _vp, _i, _i, _vp]),
-    "gvcnn_score_bin": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "gvcnn_score_bin": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_score_bin_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "gvcnn_bins_from_scores": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "gvcnn_bins_from_scores": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_bins_to_scheme": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "gvcnn_scheme_to_bins": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gvcnn_group_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -43,6 +52,8 @@ SIGNATURES = {
                                  _i, _i, _i64, _i, _i, _i, _i, _vp]),
     "gvcnn_grouping_fusion_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "gvcnn_grouping_fusion_batch_fwd": (_i, [_vp] * 13 + [_i, _i, _i, _i64, _i, _i, _i, _f, _i, _i, _i, _i, _i, _i64,
+                                                       _vp, _vp, _vp]),
     "gvcnn_pool_fuse_gap_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gvcnn_pool_fuse_gap_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "gvcnn_pool_fuse_gap_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -51,9 +62,17 @@ SIGNATURES = {
     "gvcnn_score_weight_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "gvcnn_view_score_bwd_workspace_bytes": (_sz, [_i, _i]),
     "gvcnn_view_score_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
-    "gvcnn_host_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i, _i]),
-    "gvcnn_grouping_fusion_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                        _i, _i, _i, _i64, _i, _i, _f, _i, _i, _vp, _sz]),
+    "gvcnn_comm_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp]),
+    "gvcnn_comm_connect": (_i, [_vp, _vp]),
+    "gvcnn_comm_allreduce_f32": (_i, [_vp, _vp, _i, _vp]),
+    "gvcnn_comm_allreduce_scaled_f32": (_i, [_vp, _vp, _i, _f, _vp]),
+    "gvcnn_comm_error": (_i, [_vp]),
+    "gvcnn_comm_destroy": (_i, [_vp]),
+    "gvcnn_host_pipeline_create": (_i, [ctypes.POINTER(_vp), _i]),
+    "gvcnn_host_pipeline_destroy": (_i, [_vp]),
+    "gvcnn_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64, _i, _i, _i]),
+    "gvcnn_grouping_fusion_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i64, _vp, _vp, _i, _vp, _sz]),
 }
 
 _lib = None

@@ -1,7 +1,6 @@
 // extern "C" surface of libgvcnn_sm100.so (declared in include/gvcnn_b200.h):
-// argument validation, layout -> per-view pointer table, kernel launches, and
-// the chunked host-buffer pipeline.  Nothing here touches torch.
-#include <atomic>
+// argument validation, layout -> per-view pointer table, kernel launches.  The
+// chunked host-buffer pipeline is in host_pipeline.cu.  Nothing here touches torch.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -9,8 +8,6 @@
 using namespace gvcnn;
 
 namespace {
-
-std::atomic<int> g_pool_variant{0};
 
 size_t elt_size(int dtype) { return dtype == GVCNN_F32 ? 4 : 2; }
 
@@ -86,6 +83,7 @@ const char *gvcnn_strerror(int code)
     case GVCNN_E_BAD_MODE: return "unsupported pool / mode value";
     case GVCNN_E_WORKSPACE: return "workspace too small";
     case GVCNN_E_UNSUPPORTED: return "shapes not supported by this specialised entry point (use the general one)";
+    case GVCNN_E_COMM_TIMEOUT: return "gvcnn_comm: a peer rank did not arrive (all-reduce wait timed out)";
     default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -105,13 +103,6 @@ int gvcnn_check_device(void)
         return GVCNN_E_NO_DEVICE;
     }
     return major == 10 ? 0 : GVCNN_E_NO_DEVICE;
-}
-
-int gvcnn_set_pool_variant(int variant)
-{
-    if (variant < 0 || variant > 3) return GVCNN_E_BAD_MODE;
-    g_pool_variant.store(variant);
-    return 0;
 }
 
 int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x, int B, int V, int C,
@@ -136,22 +127,22 @@ int gvcnn_batch_sum_x(const float *x, float *xsum, int B, int V, void *stream)
     return launch_batch_sum_x(x, xsum, B, V, static_cast<cudaStream_t>(stream));
 }
 
-int gvcnn_score_bin(const float *x, float denom, float *scores, int32_t *bins, int32_t *flags, int32_t *status,
-                    int64_t n, int G, int edge_ulps, int clamp, void *stream)
+int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                    int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, void *stream)
 {
-    if (!x || !bins || n <= 0 || G <= 0) return GVCNN_E_BAD_ARG;
+    if (!x || !bins || n <= 0 || G <= 0 || multiplier < 0) return GVCNN_E_BAD_ARG;
     if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
     if (edge_ulps < 0) return GVCNN_E_BAD_ARG;
-    return launch_score_bin(x, denom, scores, bins, flags, status, n, G, edge_ulps, clamp, false,
+    return launch_score_bin(x, denom, x_mean, scores, bins, flags, status, n, G, multiplier, edge_ulps, clamp, false,
                             static_cast<cudaStream_t>(stream));
 }
 
 int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, int32_t *status, int64_t n,
-                           int G, int edge_ulps, int clamp, void *stream)
+                           int G, int multiplier, int edge_ulps, int clamp, void *stream)
 {
-    if (!scores || !bins || n <= 0 || G <= 0 || edge_ulps < 0) return GVCNN_E_BAD_ARG;
+    if (!scores || !bins || n <= 0 || G <= 0 || multiplier < 0 || edge_ulps < 0) return GVCNN_E_BAD_ARG;
     if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
-    return launch_score_bin(scores, 1.0f, nullptr, bins, flags, status, n, G, edge_ulps, clamp, true,
+    return launch_score_bin(scores, 1.0f, nullptr, nullptr, bins, flags, status, n, G, multiplier, edge_ulps, clamp, true,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -199,7 +190,9 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     int rc = check_dims(B, V, D, G, dtype);
     if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!bins || !S || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
-    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    const int variant = GVCNN_POOL_VARIANT_OF(pool);
+    pool &= 0xff;
+    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 3) return GVCNN_E_BAD_MODE;
     const size_t es = elt_size(dtype);
     if (!is_aligned(S, es) || !is_aligned(bins, 4)) return GVCNN_E_MISALIGNED;
     ViewPtrs fp;
@@ -211,16 +204,15 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     al = al && is_aligned(S, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8)) &&
          (!group_desc || is_aligned(group_desc, 16));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
-    const int variant = g_pool_variant.load();
-    if (al && (!weights || empty_fill == 0.0f) && !group_desc && (variant == 0 || variant == 3)) {
-        // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu); with caller-supplied weights only
-        // when empty groups contribute nothing (empty_fill == 0, e.g. paper mode)
+    if (al && !group_desc && (variant == 0 || variant == 3)) {
+        // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu), with the reference's own weights or
+        // caller-supplied ones (model.group_fusion's second argument; empty groups then contribute w_g * fill)
         rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, weights, weight_stride_b, S, tie_mask, status, B, V, D, G, pool,
                                        empty_fill, dtype, static_cast<cudaStream_t>(stream));
         if (rc != -1000) return rc;
     }
     return launch_pool_fuse_fwd(fp, sb, bins, bin_stride_b, S, group_desc, tie_mask, weights, weight_stride_b, status, B, V, D, G, pool, empty_fill,
-                                dtype, al, g_pool_variant.load(), static_cast<cudaStream_t>(stream));
+                                dtype, al, variant, static_cast<cudaStream_t>(stream));
 }
 
 int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_b, const float *weights,
@@ -230,7 +222,9 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     int rc = check_dims(B, V, D, G, dtype);
     if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!dS || !bins || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
-    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    const int variant = GVCNN_POOL_VARIANT_OF(pool);
+    pool &= 0xff;
+    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 3) return GVCNN_E_BAD_MODE;
     if (pool == GVCNN_POOL_MAX && !tie_mask) return GVCNN_E_BAD_ARG;
     const size_t es = elt_size(dtype);
     if (!is_aligned(dS, es) || !is_aligned(bins, 4)) return GVCNN_E_MISALIGNED;
@@ -241,7 +235,6 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     if (rc) return rc;
     al = al && is_aligned(dS, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
-    const int variant = g_pool_variant.load();
     if (al && (variant == 0 || variant == 3)) {
         // fast path: V-templated kernel (pool_bwd_fast.cu)
         rc = launch_pool_fuse_bwd_fast(dS, bins, bin_stride_b, tie_mask, weights, weight_stride_b, gp, sb, status, B, V, D, G, pool, dtype,
@@ -263,7 +256,7 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
     int rc = check_dims(B, V, D, G, dtype);
     if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (C <= 0 || !W || !bias || !scores || !bins || !S || edge_ulps < 0) return GVCNN_E_BAD_ARG;
-    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    if ((pool & 0xff) != GVCNN_POOL_MAX && (pool & 0xff) != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     const size_t es = elt_size(dtype);
     ViewPtrs rp, fp;
     int64_t rsb, fsb;
@@ -281,6 +274,45 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
                              stream);
     if (rc) return rc;
     return gvcnn_pool_fuse_fwd(F, bins, V, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
+                               f_layout, dtype, stream);
+}
+
+// ---------------------------------------------------------------------------
+// whole forward, reference-literal: ONE scheme per batch (tf.reduce_mean over the batch, nets/model.py:146)
+// ---------------------------------------------------------------------------
+int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *bias, const void *F, float *x,
+                                    float *xsum, float *x_mean, float *scores, int32_t *bins, int32_t *flags, void *S,
+                                    uint8_t *tie_mask, int32_t *status, int B, int V, int C, int64_t D, int G,
+                                    int multiplier, int pool, float empty_fill, int r_layout, int f_layout, int dtype,
+                                    int edge_ulps, int clamp, int64_t global_count, gvcnn_exchange_fn exchange,
+                                    void *exchange_user, void *stream)
+{
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc && rc != kEmptyBatch) return rc;
+    const bool empty = rc == kEmptyBatch;
+    if (empty && !exchange) return 0;  // with an exchange the other ranks are waiting for this one's (zero) sums
+    if (C <= 0 || !W || !bias || !xsum || !scores || !bins || edge_ulps < 0 || multiplier < 0) return GVCNN_E_BAD_ARG;
+    if (!empty && (!x || !S)) return GVCNN_E_BAD_ARG;
+    if (global_count < B || global_count <= 0) return GVCNN_E_BAD_ARG;
+    if ((pool & 0xff) != GVCNN_POOL_MAX && (pool & 0xff) != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (empty) {
+        const cudaError_t e = cudaMemsetAsync(xsum, 0, (size_t)V * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        rc = gvcnn_view_score_fwd(R, W, bias, x, B, V, C, r_layout, dtype, stream);
+        if (rc) return rc;
+        rc = gvcnn_batch_sum_x(x, xsum, B, V, stream);
+        if (rc) return rc;
+    }
+    if (exchange) {  // SURVEY.md 8e collective (2): every rank bins the same global-batch mean
+        rc = exchange(exchange_user, xsum, V, stream);
+        if (rc) return rc;
+    }
+    rc = gvcnn_score_bin(xsum, (float)global_count, x_mean, scores, bins, flags, status, V, G, multiplier, edge_ulps,
+                         clamp, stream);
+    if (rc || empty) return rc;
+    return gvcnn_pool_fuse_fwd(F, bins, 0, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
                                f_layout, dtype, stream);
 }
 
@@ -400,150 +432,6 @@ int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *
     return launch_view_score_bwd(rp, sb, dx, W, dW, dbias, drp, dsb, dR ? 1 : 0, static_cast<float *>(workspace),
                                  GVCNN_SCORE_BWD_SLICES, B, V, C, dtype, al && al2,
                                  static_cast<cudaStream_t>(stream));
-}
-
-// ---------------------------------------------------------------------------
-// host-buffer pipeline
-// ---------------------------------------------------------------------------
-namespace {
-constexpr int kHostBufs = 3;
-size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
-
-struct ChunkLayout {
-    size_t R, F, S, scores, bins, dS, mask, dF, total;
-};
-ChunkLayout chunk_layout(int cs, int V, int C, int64_t D, int dtype, int training)
-{
-    const size_t es = elt_size(dtype);
-    ChunkLayout L{};
-    size_t o = 0;
-    L.R = o; o += align_up((size_t)cs * V * C * es);
-    L.F = o; o += align_up((size_t)cs * V * D * es);
-    L.S = o; o += align_up((size_t)cs * D * es);
-    L.scores = o; o += align_up((size_t)cs * V * 4);
-    L.bins = o; o += align_up((size_t)cs * V * 4);
-    if (training) {
-        L.dS = o; o += align_up((size_t)cs * D * es);
-        L.mask = o; o += align_up((size_t)((V + 7) / 8) * cs * D);
-        L.dF = o; o += align_up((size_t)cs * V * D * es);
-    }
-    L.total = o;
-    return L;
-}
-}  // namespace
-
-size_t gvcnn_host_workspace_bytes(int chunk_shapes, int V, int C, int64_t D, int dtype, int training)
-{
-    if (chunk_shapes <= 0 || V <= 0 || C <= 0 || D <= 0) return 0;
-    return 256 + kHostBufs * chunk_layout(chunk_shapes, V, C, D, dtype, training).total;
-}
-
-int gvcnn_grouping_fusion_host(const void *R_host, const void *F_host, const float *W_dev,
-                               const float *bias_dev, void *S_host, float *scores_host, int32_t *bins_host,
-                               const void *dS_host, void *dF_host, int32_t *status_host, int B, int V, int C,
-                               int64_t D, int G, int pool, float empty_fill, int dtype, int chunk_shapes,
-                               void *d_workspace, size_t workspace_bytes)
-{
-    int rc = check_dims(B, V, D, G, dtype);
-    if (rc) return rc == kEmptyBatch ? 0 : rc;
-    if (C <= 0 || chunk_shapes <= 0 || !R_host || !F_host || !W_dev || !bias_dev || !S_host || !d_workspace)
-        return GVCNN_E_BAD_ARG;
-    if (pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
-    const int training = (dS_host && dF_host) ? 1 : 0;
-    if ((dS_host != nullptr) != (dF_host != nullptr)) return GVCNN_E_BAD_ARG;
-    if (workspace_bytes < gvcnn_host_workspace_bytes(chunk_shapes, V, C, D, dtype, training))
-        return GVCNN_E_WORKSPACE;
-    if (!is_aligned(d_workspace, 256)) return GVCNN_E_MISALIGNED;
-    rc = gvcnn_check_device();
-    if (rc) return rc;
-
-    const size_t es = elt_size(dtype);
-    const ChunkLayout L = chunk_layout(chunk_shapes, V, C, D, dtype, training);
-    char *ws = static_cast<char *>(d_workspace);
-    int32_t *d_status = reinterpret_cast<int32_t *>(ws);
-    char *bufs = ws + 256;
-
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[kHostBufs], ev_k[kHostBufs], ev_out[kHostBufs];
-    cudaError_t err = cudaSuccess;
-#define GVCNN_CK(call)                        \
-    do {                                      \
-        if (err == cudaSuccess) err = (call); \
-    } while (0)
-    GVCNN_CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    GVCNN_CK(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    GVCNN_CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < kHostBufs; ++i) {
-        ev_in[i] = ev_k[i] = ev_out[i] = nullptr;
-        GVCNN_CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        GVCNN_CK(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
-        GVCNN_CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
-    GVCNN_CK(cudaMemsetAsync(d_status, 0, GVCNN_STATUS_WORDS * sizeof(int32_t), s_k));
-
-    int krc = 0;
-    const int nchunks = (B + chunk_shapes - 1) / chunk_shapes;
-    for (int c = 0; c < nchunks && err == cudaSuccess && krc == 0; ++c) {
-        const int i = c % kHostBufs;
-        const int b0 = c * chunk_shapes;
-        const int nb = (B - b0 < chunk_shapes) ? B - b0 : chunk_shapes;
-        char *buf = bufs + (size_t)i * L.total;
-        // the buffer is free once the copy-out of the chunk that last used it is done
-        if (c >= kHostBufs) GVCNN_CK(cudaStreamWaitEvent(s_in, ev_out[i], 0));
-        GVCNN_CK(cudaMemcpyAsync(buf + L.R, static_cast<const char *>(R_host) + (size_t)b0 * V * C * es,
-                                 (size_t)nb * V * C * es, cudaMemcpyHostToDevice, s_in));
-        GVCNN_CK(cudaMemcpyAsync(buf + L.F, static_cast<const char *>(F_host) + (size_t)b0 * V * D * es,
-                                 (size_t)nb * V * D * es, cudaMemcpyHostToDevice, s_in));
-        if (training)
-            GVCNN_CK(cudaMemcpyAsync(buf + L.dS, static_cast<const char *>(dS_host) + (size_t)b0 * D * es,
-                                     (size_t)nb * D * es, cudaMemcpyHostToDevice, s_in));
-        GVCNN_CK(cudaEventRecord(ev_in[i], s_in));
-        GVCNN_CK(cudaStreamWaitEvent(s_k, ev_in[i], 0));
-        if (err != cudaSuccess) break;
-        float *d_scores = reinterpret_cast<float *>(buf + L.scores);
-        int32_t *d_bins = reinterpret_cast<int32_t *>(buf + L.bins);
-        uint8_t *d_mask = (training && pool == GVCNN_POOL_MAX) ? reinterpret_cast<uint8_t *>(buf + L.mask) : nullptr;
-        krc = gvcnn_score_bin_fwd(buf + L.R, W_dev, bias_dev, nullptr, d_scores, d_bins, nullptr, d_status, nb, V,
-                                  C, G, GVCNN_LAYOUT_BVD, dtype, 0, 1, s_k);
-        if (krc == 0)
-            krc = gvcnn_pool_fuse_fwd(buf + L.F, d_bins, V, nullptr, 0, buf + L.S, nullptr, d_mask, d_status, nb, V, D, G, pool,
-                                      empty_fill, GVCNN_LAYOUT_BVD, dtype, s_k);
-        if (krc == 0 && training)
-            krc = gvcnn_pool_fuse_bwd(buf + L.dS, d_bins, V, nullptr, 0, d_mask, buf + L.dF, d_status, nb, V, D, G, pool,
-                                      GVCNN_LAYOUT_BVD, dtype, s_k);
-        if (krc != 0) break;
-        GVCNN_CK(cudaEventRecord(ev_k[i], s_k));
-        GVCNN_CK(cudaStreamWaitEvent(s_out, ev_k[i], 0));
-        GVCNN_CK(cudaMemcpyAsync(static_cast<char *>(S_host) + (size_t)b0 * D * es, buf + L.S,
-                                 (size_t)nb * D * es, cudaMemcpyDeviceToHost, s_out));
-        if (scores_host)
-            GVCNN_CK(cudaMemcpyAsync(scores_host + (size_t)b0 * V, d_scores, (size_t)nb * V * 4,
-                                     cudaMemcpyDeviceToHost, s_out));
-        if (bins_host)
-            GVCNN_CK(cudaMemcpyAsync(bins_host + (size_t)b0 * V, d_bins, (size_t)nb * V * 4,
-                                     cudaMemcpyDeviceToHost, s_out));
-        if (training)
-            GVCNN_CK(cudaMemcpyAsync(static_cast<char *>(dF_host) + (size_t)b0 * V * D * es, buf + L.dF,
-                                     (size_t)nb * V * D * es, cudaMemcpyDeviceToHost, s_out));
-        GVCNN_CK(cudaEventRecord(ev_out[i], s_out));
-    }
-    // drain everything before touching host outputs / destroying streams
-    if (s_in) cudaStreamSynchronize(s_in);
-    if (s_k) GVCNN_CK(cudaStreamSynchronize(s_k));
-    if (s_out) GVCNN_CK(cudaStreamSynchronize(s_out));
-    if (status_host && err == cudaSuccess && krc == 0)
-        GVCNN_CK(cudaMemcpy(status_host, d_status, GVCNN_STATUS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost));
-#undef GVCNN_CK
-    for (int i = 0; i < kHostBufs; ++i) {
-        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-        if (ev_k[i]) cudaEventDestroy(ev_k[i]);
-        if (ev_out[i]) cudaEventDestroy(ev_out[i]);
-    }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_k) cudaStreamDestroy(s_k);
-    if (s_out) cudaStreamDestroy(s_out);
-    if (krc != 0) return krc;
-    return (int)err;
 }
 
 }  // extern "C"

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "gvcnn_b200.h"
 
 namespace gvcnn {
@@ -215,6 +218,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch.
+template <auto Kern>
+inline cudaError_t ensure_dyn_smem(int bytes)
+{
+    static std::atomic<int> granted[64];  // zero-initialised; bytes already granted, per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && granted[dev].load(std::memory_order_relaxed) >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev].store(bytes, std::memory_order_relaxed);
+    return e;
+}
+
+// A/B tuning knobs are environment variables read ONCE per process (first use), never per launch.
+inline int env_int_once(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 // ---- exact division with a precomputed reciprocal -----------------------------
 // a / b, correctly rounded (== __fdiv_rn(a, b)), given rcp_b = __frcp_rn(b) =
 // RN(1/b): q = RN(a * rcp_b) is within 1 ulp of a / b, the remainder r = a - b*q
@@ -301,15 +325,17 @@ template <> struct Elem<__nv_bfloat16> {
 // ---- score epilogue (shared by score.cu and score_ring.cu) --------------------------
 // s = |x| / (1 + |x|) == sigmoid(log|x|); bin = (int)(s * G) with a float32
 // product (NumPy scalar semantics of model.py:23).  Returns the flag bits.
+// `mult` (> 0) replaces G as the multiplier: the reference hard-codes `* 10` (nets/model.py:23) whatever
+// num_group is; the range check stays against G (an index into the G scheme rows).
 __device__ __forceinline__ int score_and_bin(float x, float denom, int G, int edge_ulps, int clamp,
-                                             float &s_out, int &bin_out, bool x_is_score = false)
+                                             float &s_out, int &bin_out, bool x_is_score = false, int mult = 0)
 {
     const float xm = __fdiv_rn(x, denom);
     const float ax = fabsf(xm);
     float s = x_is_score ? x : (isinf(ax) ? 1.0f : __fdiv_rn(ax, __fadd_rn(1.0f, ax)));
     int flags = 0;
     int bin;
-    const float fg = (float)G;
+    const float fg = (float)(mult > 0 ? mult : G);
     if (isnan(s)) {
         flags |= GVCNN_FLAG_NAN;
         bin = clamp ? 0 : INT32_MIN;
@@ -349,8 +375,8 @@ int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const fl
                       int G, int dtype, bool aligned16, bool fuse_bin, int edge_ulps, int clamp,
                       cudaStream_t st);
 int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st);
-int launch_score_bin(const float *x, float denom, float *scores, int32_t *bins, int32_t *flags,
-                     int32_t *status, int64_t n, int G, int edge_ulps, int clamp, bool x_is_score,
+int launch_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                     int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, bool x_is_score,
                      cudaStream_t st);
 int launch_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, cudaStream_t st);
 int launch_scheme_to_bins(const int32_t *scheme, int32_t *bins, int32_t *status, int rows, int V, int G,

@@ -381,7 +381,7 @@ static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
 #define GVCNN_LAUNCH_CHUNKED_NT(POOL_, MASK_, NT_)                                                             \
     do {                                                                                                       \
         auto kern = pool_fuse_fwd_chunked_kernel<T, POOL_, MASK_, NT_>;                                        \
-        e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);              \
+        e2 = ensure_dyn_smem<pool_fuse_fwd_chunked_kernel<T, POOL_, MASK_, NT_>>((int)smemv);                  \
         if (e2 == cudaSuccess)                                                                                 \
             kern<<<(unsigned)(B * tilesv), NT_, smemv, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),       \
                                                             static_cast<T *>(Pout), mask, weights, w_sb, status, \
@@ -415,7 +415,7 @@ static int launch_fwd_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
     do {                                                                                                   \
         auto kern = pool_fuse_fwd_kernel<T, VEC_, POOL_, MASK_, BULK_>;                                    \
         if (smem + 8192 > 48 * 1024)                                                                            \
-            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+            err = ensure_dyn_smem<pool_fuse_fwd_kernel<T, VEC_, POOL_, MASK_, BULK_>>((int)smem);         \
         if (err == cudaSuccess)                                                                            \
             kern<<<(unsigned)(B * tiles), nt, smem, st>>>(fp, f_sb, bins, bin_sb, static_cast<T *>(S),      \
                                                           static_cast<T *>(Pout), mask, weights, w_sb,     \

@@ -24,8 +24,6 @@
 // in scripts/ring_trace_probe.cu) but is neutral to slower once launches run back to back, and slower for small
 // tiles (V = 6) and shallow rings (V = 20) because the compiler emits the one-lane atomic in its warp-aggregated
 // form, which waits for the counter on the spot.
-#include <cstdlib>
-
 #include "ring_common.cuh"
 
 namespace gvcnn {
@@ -68,6 +66,7 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     constexpr uint32_t kStageBytes = kRowStride * (uint32_t)V;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ RingPlan plans[kMaxStages];
+    __shared__ RingWts wts_s[WTS ? kMaxStages : 1];  // whole weight rows: only the caller-supplied-weights variant
     __shared__ int32_t sorted_bin[32];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -149,6 +148,8 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
                     for (int g = 0; g < G; ++g) sw = __fadd_rn(sw, __ldg(wrow + g));
                     plans[s].sumw = sw;
                 }
+                if (fill != 0.0f)  // empty groups contribute w_g * fill: the consumers need the whole row
+                    for (int g = lane; g < G; g += 32) wts_s[s].wall[g] = __ldg(wrow + g);
             }
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full_bar[s], row_bytes * (uint32_t)V);
@@ -184,7 +185,8 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         if (threadIdx.x == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(1);
 
         float acc[E];
-        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc, WTS);
+        ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, active, mask, B, D, out_off, acc, WTS,
+                                                        WTS ? wts_s[s].wall : nullptr);
         const float sw_given = WTS ? plans[s].sumw : 0.0f;
         // every lane of the warp is done reading the slot: hand it back to the producer
         __syncwarp();
@@ -228,13 +230,11 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
     // shared memory an SM can give to MINB co-resident CTAs of this kernel (1 KB reserved + ~1.3 KB static each)
     int stages = (int)(((226 * 1024) / MINB - 3 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
-    if (const char *env = getenv("GVCNN_RING_STAGES")) {  // tuning knob for A/B runs
-        const int want = atoi(env);
-        if (want >= 2 && want <= stages) stages = want;
-    }
+    static const int env_stages = env_int_once("GVCNN_RING_STAGES", 0);  // tuning knobs for A/B runs, read once
+    static const int env_l2hint = env_int_once("GVCNN_RING_L2HINT", 1);
+    if (env_stages >= 2 && env_stages <= stages) stages = env_stages;
     if (stages < 2) return -1000;
-    int l2_hint = 1;
-    if (const char *env = getenv("GVCNN_RING_L2HINT")) l2_hint = atoi(env);  // tuning knob for A/B runs
+    const int l2_hint = env_l2hint;
     const int64_t td = (int64_t)NCONS * E;
     const int64_t tps = (D + td - 1) / td;
     const int64_t tiles = (int64_t)B * tps;
@@ -247,7 +247,7 @@ static int launch_ring_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
 #define GVCNN_LAUNCH_RING(POOL_, MASK_, WTS_)                                                                \
     do {                                                                                                     \
         auto kern = pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, WTS_, V, NCONS, MINB>;                        \
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        err = ensure_dyn_smem<pool_fuse_fwd_ring_kernel<T, POOL_, MASK_, WTS_, V, NCONS, MINB>>((int)smem);  \
         if (err == cudaSuccess)                                                                              \
             err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
                              bin_sb, weights, w_sb, static_cast<T *>(S), mask, status, B, D, G, fill,        \
@@ -298,6 +298,7 @@ int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *b
                               float fill, int dtype, cudaStream_t st)
 {
     if (V > 32 || G > 255) return -1000;
+    if (weights && fill != 0.0f && G > kRingMaxWtsGroups) return -1000;  // weight row per ring slot (RingWts)
     if (dtype == GVCNN_F32) {
         if (D % 4) return -1000;
         return launch_ring_t<float>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, V, D, G, pool, fill, st);

@@ -197,7 +197,7 @@ static int launch_gap_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, i
 #define GVCNN_LAUNCH_GAP(POOL_, MASK_)                                                                        \
     do {                                                                                                      \
         auto kern = pool_fuse_gap_fwd_kernel<T, POOL_, MASK_, V, NCONS, MINB>;                                \
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        err = ensure_dyn_smem<pool_fuse_gap_fwd_kernel<T, POOL_, MASK_, V, NCONS, MINB>>((int)smem);          \
         if (err == cudaSuccess)                                                                               \
             err = launch_pdl(kern, dim3(grid), dim3(NCONS + kRingProducerThreads), smem, st, fp, f_sb, bins,  \
                              bin_sb, partial, mask, status, B, C, HW, G, fill, CB, nsplit, pps, (int)units,   \

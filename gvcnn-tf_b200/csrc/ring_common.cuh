@@ -18,6 +18,14 @@ struct __align__(16) RingPlan {
     float sumw;           // caller-supplied weights only: sum of all G weights (left to right)
 };
 
+// Caller-supplied weights with empty_fill != 0 (model.group_fusion(view_pooling(...), group_weight(...)), the
+// reference's own call sequence, nets/model.py:154-157): an empty group g contributes w[g] * fill, so the consumers
+// need the whole weight row, not only the non-empty groups' weights.  One row per ring slot.
+constexpr int kRingMaxWtsGroups = 64;
+struct __align__(16) RingWts {
+    float wall[kRingMaxWtsGroups];
+};
+
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
 {
     const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
@@ -42,7 +50,8 @@ template <typename T, int POOL, bool MASK, int V, uint32_t ROWSTRIDE>
 __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, const RingPlan &plan_s, const float fill,
                                                   const bool active, uint8_t *__restrict__ mask, const int B,
                                                   const int64_t D, const int64_t out_off,
-                                                  float (&acc)[Elem<T>::kVec], const bool wts = false)
+                                                  float (&acc)[Elem<T>::kVec], const bool wts = false,
+                                                  const float *wall = nullptr)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
@@ -71,6 +80,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) me2[i] = me2b[i] = 0u;
         int cnt = 0;
+        int gcur = 0;  // group index the walk has reached (caller-supplied weights of empty groups)
 #pragma unroll
         for (int k = 0; k <= V; ++k) {
             if (k == V || k == 0 || ((fm >> k) & 1u)) {
@@ -98,13 +108,16 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
+                        const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;  // w_g * P_g, P_g = fill
 #pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
                     }
+                    gcur += (int)nskip;
                 }
                 if (k < V) {
                     m2[0] = raw[k].x; m2[1] = raw[k].y; m2[2] = raw[k].z; m2[3] = raw[k].w;
                     cnt = 1;
+                    ++gcur;
                 }
             } else {
                 const uint4 r = raw[k < V ? k : 0];
@@ -153,6 +166,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #pragma unroll
         for (int e = 0; e < E; ++e) me[e] = 0u;
         int cnt = 0;
+        int gcur = 0;  // group index the walk has reached (caller-supplied weights of empty groups)
 #pragma unroll
         for (int k = 0; k <= V; ++k) {
             if (k == V || k == 0 || ((fm >> k) & 1u)) {  // uniform: a group ends / starts here
@@ -173,17 +187,20 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
                 }
-                if (fill != 0.0f) {  // empty groups in between / after: w = 1, P = fill
+                if (fill != 0.0f) {  // empty groups in between / after: w = 1 (or given), P = fill
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
+                        const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;  // w_g * P_g, P_g = fill
 #pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], fill);
+                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
                     }
+                    gcur += (int)nskip;
                 }
                 if (k < V) {
                     Elem<T>::unpack(raw[k], m);
                     cnt = 1;
+                    ++gcur;
                 }
             } else {
                 float x[E];

@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(256) batch_sum_x_kernel(const float *__restric
 {
     __shared__ float warp_sum[8];
     const int v = blockIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
     float acc = 0.0f;
     for (int b = threadIdx.x; b < B; b += 256) acc = __fadd_rn(acc, x[(int64_t)b * V + v]);
 #pragma unroll
@@ -188,17 +190,21 @@ __global__ void __launch_bounds__(256) batch_sum_x_kernel(const float *__restric
 }
 
 __global__ void __launch_bounds__(256) score_bin_kernel(const float *__restrict__ x, const float denom,
-                                                        float *__restrict__ scores,
+                                                        float *__restrict__ x_mean, float *__restrict__ scores,
                                                         int32_t *__restrict__ bins,
                                                         int32_t *__restrict__ flag_out, int32_t *status,
-                                                        const int64_t n, const int G, const int edge_ulps,
-                                                        const int clamp, const bool x_is_score)
+                                                        const int64_t n, const int G, const int mult,
+                                                        const int edge_ulps, const int clamp,
+                                                        const bool x_is_score)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
     if (i >= n) return;
     float s;
     int bin;
-    const int flags = score_and_bin(x[i], denom, G, edge_ulps, clamp, s, bin, x_is_score);
+    const int flags = score_and_bin(x[i], denom, G, edge_ulps, clamp, s, bin, x_is_score, mult);
+    if (x_mean) x_mean[i] = __fdiv_rn(x[i], denom);  // tf.reduce_mean(raw), nets/model.py:146
     if (scores) scores[i] = s;
     bins[i] = bin;
     publish(flags, flag_out ? flag_out + i : nullptr, status);
@@ -259,17 +265,19 @@ int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const fl
 
 int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st)
 {
-    batch_sum_x_kernel<<<V, 256, 0, st>>>(x, xsum, B, V);
+    const cudaError_t err = launch_pdl(batch_sum_x_kernel, dim3(V), dim3(256), 0, st, x, xsum, B, V);
+    if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
 
-int launch_score_bin(const float *x, float denom, float *scores, int32_t *bins, int32_t *flags,
-                     int32_t *status, int64_t n, int G, int edge_ulps, int clamp, bool x_is_score,
+int launch_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                     int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, bool x_is_score,
                      cudaStream_t st)
 {
     const unsigned grid = (unsigned)((n + 255) / 256);
-    score_bin_kernel<<<grid, 256, 0, st>>>(x, denom, scores, bins, flags, status, n, G, edge_ulps, clamp,
-                                           x_is_score);
+    const cudaError_t err = launch_pdl(score_bin_kernel, dim3(grid), dim3(256), 0, st, x, denom, x_mean, scores, bins,
+                                       flags, status, n, G, multiplier, edge_ulps, clamp, x_is_score);
+    if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
 

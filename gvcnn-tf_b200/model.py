@@ -30,9 +30,45 @@ __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion", "view_scores",
     "score_bin", "pool_fuse", "grouping_fusion", "GroupDescriptors", "ScoreResult",
     "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status", "grouping_fusion_paper", "pool_fuse_gap",
+    "make_exchange",
 ]
 
 _POOL = {"max": C.POOL_MAX, "mean": C.POOL_MEAN}
+_SCORE_REDUCE = {"shape": C.SCORE_REDUCE_SHAPE, "batch": C.SCORE_REDUCE_BATCH}
+
+
+def _pool_code(pool: str, variant: int = 0) -> int:
+    """`pool` argument of the C ABI; `variant` (tests / A-B runs only) rides in bits 8..11 (GVCNN_POOL_VARIANT)."""
+    return C.pool_variant(_POOL[pool], variant)
+
+
+class _DevArray:
+    """A raw device pointer as something torch.as_tensor understands (CUDA array interface), so a C callback
+    that receives `float *xsum_dev` can hand it to torch.distributed without a copy."""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def make_exchange(process_group):
+    """gvcnn_exchange_fn for a torch.distributed process group: all-reduces (sum) the V per-view partial sums in
+    place, ordered on the stream the library is working on (SURVEY.md 8e collective (2)).  Returns
+    (ctypes callback, keep-alive) - keep the second value referenced while the callback can still be called."""
+    import torch.distributed as dist
+
+    def _exchange(_user, xsum_ptr, n, stream_ptr):
+        try:
+            t = torch.as_tensor(_DevArray(xsum_ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+            ext = torch.cuda.ExternalStream(stream_ptr) if stream_ptr else torch.cuda.default_stream()
+            with torch.cuda.stream(ext):
+                dist.all_reduce(t, group=process_group)
+            return 0
+        except Exception:                                           # noqa: BLE001 - nothing may unwind through C
+            import traceback
+            traceback.print_exc()
+            return 1                                                # cudaErrorInvalidValue: surfaces as GvcnnError
+    cb = C.EXCHANGE_FN(_exchange)
+    return cb, (_exchange, cb)
 
 
 # --------------------------------------------------------------------------
@@ -128,6 +164,8 @@ def raise_for_status(status: torch.Tensor, num_group: int):
     """Turns the device status words into the reference's exceptions
     (nets/model.py:23): NaN score -> ValueError, bin >= num_group -> IndexError.
     Synchronises (one 16-byte device->host copy)."""
+    if status is None:
+        raise RuntimeError("no status words were recorded: call with check=True or pass status=")
     st = status.tolist()
     if st[C.STATUS_NAN]:
         raise ValueError("cannot convert float NaN to integer (%d NaN view scores)" % st[C.STATUS_NAN])
@@ -159,8 +197,13 @@ class ScoreResult:
 # --------------------------------------------------------------------------
 # score + bin                                           nets/model.py:143-148, :23
 # --------------------------------------------------------------------------
+def _new_status(dev):
+    return torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+
+
 def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulps=1, clamp=False,
-              check=True, process_group=None) -> ScoreResult:
+              check=True, process_group=None, multiplier=None, status=None, exchange=None,
+              global_count=None) -> ScoreResult:
     """Per-view discrimination score and bin.
 
     R: raw view descriptors after GAP (nets/model.py:144), [B, V, C] ('bvd'),
@@ -171,6 +214,11 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
        tf.reduce_mean over the batch (nets/model.py:146), bins [1, V]; with a
        torch.distributed ``process_group`` the per-view sums are all-reduced
        first so every rank bins the same global-batch mean.
+    multiplier: None = num_group; 10 = the reference's hard-coded ``score * 10`` (nets/model.py:23;
+       'batch' mode only - the fused per-shape kernel multiplies by num_group).
+    status: optional persistent int32[4] device tensor the counters are ADDED to (check it every N steps
+       with raise_for_status instead of synchronising every step); with check=False and no status given
+       nothing is recorded.
     """
     rv = _Views(R, layout, "R")
     _require_cuda(W, "W"), _require_cuda(b, "b")
@@ -182,14 +230,15 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
                          % ((rv.V, rv.D), tuple(Wc.shape), tuple(bc.shape)))
     dev = rv.device
     L = C.lib()
-    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    if status is None and check:
+        status = _new_status(dev)
     dt = _dtype_code(rv.dtype)
     with torch.cuda.device(dev):
         if score_reduce == "shape":
-            x = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
-            scores = torch.empty_like(x)
-            bins = torch.empty((rv.B, rv.V), dtype=torch.int32, device=dev)
-            flags = torch.empty_like(bins)
+            if multiplier not in (None, num_group):
+                raise ValueError("multiplier is only selectable with score_reduce='batch' or through group_scheme")
+            buf = torch.empty((4, rv.B, rv.V), dtype=torch.int32, device=dev)      # x, scores, bins, flags: one allocation
+            x, scores, bins, flags = buf[0].view(torch.float32), buf[1].view(torch.float32), buf[2], buf[3]
             C.check(L.gvcnn_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(x), _ptr(scores), _ptr(bins),
                                           _ptr(flags), _ptr(status), rv.B, rv.V, rv.D, num_group,
                                           rv.layout, dt, edge_ulps, int(clamp), _stream()),
@@ -198,23 +247,29 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
             xb = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
             C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb), rv.B, rv.V, rv.D,
                                            rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
-            xsum = torch.empty((1, rv.V), dtype=torch.float32, device=dev)
-            C.check(L.gvcnn_batch_sum_x(_ptr(xb), _ptr(xsum), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
-            denom = rv.B
-            if process_group is not None:
+            buf = torch.empty((5, 1, rv.V), dtype=torch.int32, device=dev)
+            xsum, x, scores = (buf[i].view(torch.float32) for i in range(3))
+            bins, flags = buf[3], buf[4]
+            if rv.B > 0:
+                C.check(L.gvcnn_batch_sum_x(_ptr(xb), _ptr(xsum), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
+            else:
+                xsum.zero_()
+            denom = rv.B if global_count is None else int(global_count)
+            if exchange is not None:                                 # a gvcnn_exchange_fn (e.g. parallel.P2PComm)
+                fn, user = exchange
+                C.check(fn(user, _ptr(xsum), rv.V, _stream()), "exchange")
+            elif process_group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(xsum, group=process_group)
-                cnt = torch.tensor([rv.B], dtype=torch.int64, device=dev)
-                dist.all_reduce(cnt, group=process_group)
-                denom = int(cnt.item())
-            x = xsum
-            scores = torch.empty_like(x)
-            bins = torch.empty((1, rv.V), dtype=torch.int32, device=dev)
-            flags = torch.empty_like(bins)
-            C.check(L.gvcnn_score_bin(_ptr(x), ctypes.c_float(float(denom)), _ptr(scores), _ptr(bins),
-                                      _ptr(flags), _ptr(status), rv.V, num_group, edge_ulps, int(clamp),
-                                      _stream()), "gvcnn_score_bin")
-            x = x / float(denom)
+                if global_count is None:
+                    cnt = torch.tensor([rv.B], dtype=torch.int64, device=dev)
+                    dist.all_reduce(cnt, group=process_group)
+                    denom = int(cnt.item())
+            if denom <= 0:
+                raise ValueError("score_reduce='batch' over an empty (global) batch")
+            C.check(L.gvcnn_score_bin(_ptr(xsum), ctypes.c_float(float(denom)), _ptr(x), _ptr(scores), _ptr(bins),
+                                      _ptr(flags), _ptr(status), rv.V, num_group, int(multiplier or 0), edge_ulps,
+                                      int(clamp), _stream()), "gvcnn_score_bin")
         else:
             raise ValueError("score_reduce must be 'shape' or 'batch'")
     res = ScoreResult(x, scores, bins, flags, status, num_group)
@@ -223,31 +278,47 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
     return res
 
 
-def view_scores(raw_view_descriptors, W, b, score_reduce="batch", layout=None):
+def view_scores(raw_view_descriptors, W, b, score_reduce="batch", layout=None, process_group=None):
     """view_discrimination_scores as nets/model.py:144-148 produces them:
     sigmoid(log|mean_n(Dense(1)(raw))|) - [1, V] for the literal 'batch' mode,
     [B, V] for 'shape'."""
     return score_bin(raw_view_descriptors, W, b, 1, score_reduce=score_reduce, layout=layout,
-                     edge_ulps=0, clamp=True, check=False).scores
+                     edge_ulps=0, clamp=True, check=False, process_group=process_group).scores
 
 
 # --------------------------------------------------------------------------
 # group_scheme / group_weight                           nets/model.py:16-41
 # --------------------------------------------------------------------------
-def _bins_from_scores(scores2d: torch.Tensor, num_group: int, clamp=False, check=True):
+# Provenance tags: group_scheme() remembers the bin map its one-hot scheme was made from, group_weight() remembers
+# the scheme its weights were counted from.  While the tagged tensors are unmodified (torch's in-place version
+# counter), view_pooling / group_weight skip the scheme -> bins conversion and its validation, and group_fusion knows
+# the weights ARE 1 + n_g and runs the kernel instantiation that computes them in registers.  Anything else (host
+# arrays, edited tensors, hand-made weights) takes the general path - same results, a few more launches.
+def _tag(t: torch.Tensor, **kw):
+    t._gvcnn_tag = dict(kw, version=t._version)
+    return t
+
+
+def _tag_of(t):
+    tag = getattr(t, "_gvcnn_tag", None) if isinstance(t, torch.Tensor) else None
+    return tag if (tag is not None and tag["version"] == t._version) else None
+
+
+def _bins_from_scores(scores2d: torch.Tensor, num_group: int, clamp=False, check=True, multiplier=None):
     L = C.lib()
     dev = scores2d.device
-    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    status = _new_status(dev) if check else None
     bins = torch.empty(scores2d.shape, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         C.check(L.gvcnn_bins_from_scores(_ptr(scores2d), _ptr(bins), None, _ptr(status), scores2d.numel(),
-                                         num_group, 0, int(clamp), _stream()), "gvcnn_bins_from_scores")
+                                         num_group, int(multiplier or 0), 0, int(clamp), _stream()),
+                "gvcnn_bins_from_scores")
     if check:
         raise_for_status(status, num_group)
     return bins
 
 
-def group_scheme(view_discrimination_score, num_group, num_views):
+def group_scheme(view_discrimination_score, num_group, num_views, multiplier=None, check=True):
     """One-hot grouping scheme.  Mirrors nets/model.py:16-25.
 
     view_discrimination_score: what the reference passes - a sequence holding
@@ -255,8 +326,10 @@ def group_scheme(view_discrimination_score, num_group, num_views):
     tensor [1, V]; a CUDA tensor [B, V] with B > 1 gives per-shape schemes
     [B, num_group, V].  Returns an int32 CUDA tensor [num_group, num_views].
     Raises IndexError when a score maps to bin >= num_group (score == 1.0) and
-    ValueError on NaN, like the reference.  The reference's hard-coded ``* 10``
-    (model.py:23) is generalised to ``* num_group`` (identical at 10).
+    ValueError on NaN, like the reference (one 16-byte device->host read; check=False skips it).
+    multiplier: the reference hard-codes ``score * 10`` (model.py:23) and only ever runs num_group == 10;
+    None generalises that to ``* num_group`` (identical at 10), ``multiplier=10`` is the literal code for any
+    num_group (bins >= num_group then raise IndexError exactly like the reference's out-of-bounds write).
     """
     s = view_discrimination_score
     if isinstance(s, torch.Tensor):
@@ -278,13 +351,14 @@ def group_scheme(view_discrimination_score, num_group, num_views):
                 s2 = torch.tensor([float(t) for t in items], dtype=torch.float32, device="cuda").reshape(1, -1)
     if s2.shape[1] != num_views:
         raise ValueError("expected %d view scores, got %d" % (num_views, s2.shape[1]))
-    bins = _bins_from_scores(s2, num_group)
+    bins = _bins_from_scores(s2, num_group, check=check, multiplier=multiplier)
     rows = bins.shape[0]
     scheme = torch.empty((rows, num_group, num_views), dtype=torch.int32, device=bins.device)
     with torch.cuda.device(bins.device):
         C.check(C.lib().gvcnn_bins_to_scheme(_ptr(bins), _ptr(scheme), rows, num_views, num_group, _stream()),
                 "gvcnn_bins_to_scheme")
-    return scheme[0] if rows == 1 else scheme
+    out = scheme[0] if rows == 1 else scheme
+    return _tag(out, kind="scheme", bins=bins, G=num_group, checked=bool(check))
 
 
 def _small_to_device(x, device, dtype, name):
@@ -301,12 +375,15 @@ def _small_to_device(x, device, dtype, name):
 
 def _scheme_to_bins(g_schemes: torch.Tensor, check=True):
     _require_cuda(g_schemes, "group_scheme")
+    tag = _tag_of(g_schemes)
+    if tag is not None and tag.get("kind") == "scheme" and (tag["checked"] or not check):
+        return tag["bins"], tag["G"]                                 # made by group_scheme and untouched since
     sc = g_schemes.to(torch.int32)
     if sc.dim() == 2:
         sc = sc[None]
     sc = sc.contiguous()
     rows, G, V = sc.shape
-    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=sc.device)
+    status = _new_status(sc.device) if check else None
     bins = torch.empty((rows, V), dtype=torch.int32, device=sc.device)
     with torch.cuda.device(sc.device):
         C.check(C.lib().gvcnn_scheme_to_bins(_ptr(sc), _ptr(bins), _ptr(status), rows, V, G, _stream()),
@@ -330,17 +407,20 @@ def group_weight(g_schemes):
     w = torch.empty((rows, G), dtype=torch.float32, device=bins.device)
     with torch.cuda.device(bins.device):
         C.check(C.lib().gvcnn_group_weight(_ptr(bins), _ptr(w), rows, V, G, _stream()), "gvcnn_group_weight")
-    return w[0] if g_schemes.dim() == 2 else w
+    out = w[0] if g_schemes.dim() == 2 else w
+    return _tag(out, kind="weight", bins=bins)
 
 
 # --------------------------------------------------------------------------
 # pooling + fusion                                      nets/model.py:44-102
 # --------------------------------------------------------------------------
 def _pool_fuse_fwd(fv: _Views, bins: torch.Tensor, G: int, pool: str, empty_fill: float,
-                   weights: Optional[torch.Tensor], want_mask: bool, want_groups: bool):
+                   weights: Optional[torch.Tensor], want_mask: bool, want_groups: bool, want_status: bool = True,
+                   variant: int = 0):
     dev = fv.device
     dt = _dtype_code(fv.dtype)
-    bins = bins.to(torch.int32).contiguous()
+    if bins.dtype != torch.int32 or not bins.is_contiguous():
+        bins = bins.to(torch.int32).contiguous()
     if bins.dim() == 1:
         bins = bins[None]
     if bins.shape[-1] != fv.V or bins.shape[0] not in (1, fv.B):
@@ -361,23 +441,22 @@ def _pool_fuse_fwd(fv: _Views, bins: torch.Tensor, G: int, pool: str, empty_fill
     if want_mask and pool == "max":
         mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
     P = torch.empty((G, fv.B, fv.D), dtype=fv.dtype, device=dev) if want_groups else None
-    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
+    status = _new_status(dev) if want_status else None
     with torch.cuda.device(dev):
         C.check(C.lib().gvcnn_pool_fuse_fwd(fv.arg, _ptr(bins), bin_stride, w_ptr, w_stride, _ptr(S), _ptr(P),
-                                            _ptr(mask), _ptr(status), fv.B, fv.V, fv.D, G, _POOL[pool],
+                                            _ptr(mask), _ptr(status), fv.B, fv.V, fv.D, G, _pool_code(pool, variant),
                                             ctypes.c_float(empty_fill), fv.layout, dt, _stream()),
                 "gvcnn_pool_fuse_fwd")
     return S, mask, P, status, bins, bin_stride, weights, w_stride
 
 
-def _pool_fuse_bwd(dS: torch.Tensor, fv_like: _Views, bins, bin_stride, weights, w_stride, mask, G, pool):
+def _pool_fuse_bwd(dS: torch.Tensor, fv_like: _Views, bins, bin_stride, weights, w_stride, mask, G, pool, variant=0):
     dS = dS.contiguous()
     out, gv = fv_like.empty_like()
-    status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dS.device)
     with torch.cuda.device(dS.device):
         C.check(C.lib().gvcnn_pool_fuse_bwd(_ptr(dS), _ptr(bins), bin_stride, _ptr(weights), w_stride,
-                                            _ptr(mask), gv.arg, _ptr(status), gv.B, gv.V, gv.D, G,
-                                            _POOL[pool], gv.layout, _dtype_code(gv.dtype), _stream()),
+                                            _ptr(mask), gv.arg, None, gv.B, gv.V, gv.D, G,
+                                            _pool_code(pool, variant), gv.layout, _dtype_code(gv.dtype), _stream()),
                 "gvcnn_pool_fuse_bwd")
     return out
 
@@ -388,16 +467,19 @@ class _PoolFuseFn(torch.autograd.Function):
     train.py:127-128, utils/train_utils.py:203-206)."""
 
     @staticmethod
-    def forward(ctx, bins, weights, G, pool, empty_fill, layout, n_views, *views):
+    def forward(ctx, bins, weights, G, pool, empty_fill, layout, want_status, variant, *views):
         is_list = layout == "list"
         fv = _Views(list(views) if is_list else views[0], None if is_list else layout, "F")
         need_grad = any(v.requires_grad for v in views)
         S, mask, _, status, bins_c, bstride, w_c, wstride = _pool_fuse_fwd(
-            fv, bins, G, pool, empty_fill, weights, want_mask=need_grad, want_groups=False)
-        ctx.fv, ctx.G, ctx.pool = fv, G, pool
+            fv, bins, G, pool, empty_fill, weights, want_mask=need_grad, want_groups=False,
+            want_status=want_status, variant=variant)
+        ctx.fv, ctx.G, ctx.pool, ctx.variant = fv, G, pool, variant
         ctx.bstride, ctx.wstride = bstride, wstride
         ctx.save_for_backward(bins_c, mask if mask is not None else torch.empty(0, device=S.device),
                               w_c if w_c is not None else torch.empty(0, device=S.device))
+        if status is None:
+            status = torch.empty(0, dtype=torch.int32, device=S.device)
         ctx.mark_non_differentiable(status)
         return S.reshape(fv.view_shape), status
 
@@ -408,13 +490,25 @@ class _PoolFuseFn(torch.autograd.Function):
         w_c = w_c if w_c.numel() else None
         fv = ctx.fv
         out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins_c, ctx.bstride, w_c, ctx.wstride, mask,
-                             ctx.G, ctx.pool)
+                             ctx.G, ctx.pool, ctx.variant)
         grads = tuple(out) if isinstance(out, list) else (out,)
-        return (None, None, None, None, None, None, None) + grads
+        return (None,) * 8 + grads
+
+
+def _run_pool_fuse(views, lay, bins, weights, G, pool, empty_fill, want_status, variant=0):
+    """Forward through autograd only when a gradient can be asked for; otherwise straight into the library
+    (saves the autograd.Function bookkeeping on the inference path)."""
+    if torch.is_grad_enabled() and any(v.requires_grad for v in views):
+        S, status = _PoolFuseFn.apply(bins, weights, G, pool, empty_fill, lay, want_status, variant, *views)
+        return S, (status if status.numel() else None)
+    fv = _Views(list(views) if lay == "list" else views[0], None if lay == "list" else lay, "F")
+    S, _, _, status, _, _, _, _ = _pool_fuse_fwd(fv, bins, G, pool, empty_fill, weights, want_mask=False,
+                                                 want_groups=False, want_status=want_status, variant=variant)
+    return S.reshape(fv.view_shape), status
 
 
 def pool_fuse(final_view_descriptors, bins, num_group, pool="max", empty_fill=1.0, layout=None,
-              group_weight=None, check=False):
+              group_weight=None, check=False, _variant=0):
     """Fused view_pooling + group_fusion (nets/model.py:44-102) from a bin map.
 
     final_view_descriptors: list of V tensors [N, ...] (the reference's layout),
@@ -428,7 +522,7 @@ def pool_fuse(final_view_descriptors, bins, num_group, pool="max", empty_fill=1.
     else:
         views, lay = (final_view_descriptors,), (layout or "bvd")
     _require_cuda(bins, "bins")
-    S, status = _PoolFuseFn.apply(bins, group_weight, num_group, pool, empty_fill, lay, len(views), *views)
+    S, status = _run_pool_fuse(views, lay, bins, group_weight, num_group, pool, empty_fill, check, _variant)
     if check:
         raise_for_status(status, num_group)
     return S
@@ -517,14 +611,17 @@ class GroupDescriptors(dict):
     """What ``view_pooling`` returns: behaves like the reference's
     ``{group index: pooled descriptor}`` dict (nets/model.py:61,72), but lazy -
     the G pooled tensors are only materialised (one kernel writing [G, B, D])
-    if somebody indexes or iterates the dict.  ``group_fusion`` recognises this
-    object and runs the single-pass fused kernel on the original views."""
+    if somebody indexes or iterates the dict.  ``group_fusion`` recognises an
+    UNEDITED object of this type and runs the single-pass fused kernel on the
+    original views; once an entry has been assigned or removed it is an
+    ordinary dict of tensors and is fused as such."""
 
     def __init__(self, views, layout, bins, num_group, pool, empty_fill):
         super().__init__()
         self._views, self._layout = views, layout
         self._bins, self._G, self._pool, self._fill = bins, num_group, pool, empty_fill
         self._done = False
+        self._edited = False
 
     def _materialise(self):
         if self._done:
@@ -532,7 +629,7 @@ class GroupDescriptors(dict):
         fv = _Views(list(self._views) if self._layout == "list" else self._views[0],
                     None if self._layout == "list" else self._layout, "F")
         _, _, P, _, _, _, _, _ = _pool_fuse_fwd(fv, self._bins, self._G, self._pool, self._fill, None,
-                                                want_mask=False, want_groups=True)
+                                                want_mask=False, want_groups=True, want_status=False)
         for g in range(self._G):
             dict.__setitem__(self, g, P[g].reshape(fv.view_shape))
         self._done = True
@@ -546,9 +643,11 @@ class GroupDescriptors(dict):
         return dict.__iter__(self)
 
     def __len__(self):
-        return self._G
+        return dict.__len__(self) if self._edited else self._G
 
     def __contains__(self, k):
+        if self._edited:
+            return dict.__contains__(self, k)
         return isinstance(k, int) and 0 <= k < self._G
 
     def items(self):
@@ -562,6 +661,31 @@ class GroupDescriptors(dict):
     def values(self):
         self._materialise()
         return dict.values(self)
+
+    def get(self, k, default=None):
+        self._materialise()
+        return dict.get(self, k, default)
+
+    # mutation: from here on this is a plain dict of tensors
+    def __setitem__(self, k, v):
+        self._materialise()
+        self._edited = True
+        dict.__setitem__(self, k, v)
+
+    def __delitem__(self, k):
+        self._materialise()
+        self._edited = True
+        dict.__delitem__(self, k)
+
+    def pop(self, *a):
+        self._materialise()
+        self._edited = True
+        return dict.pop(self, *a)
+
+    def update(self, *a, **kw):
+        self._materialise()
+        self._edited = True
+        dict.update(self, *a, **kw)
 
 
 def view_pooling(final_view_descriptors, group_scheme, pool="max", empty_fill=1.0, layout=None):
@@ -585,20 +709,53 @@ def view_pooling(final_view_descriptors, group_scheme, pool="max", empty_fill=1.
     return GroupDescriptors(views, lay, bins, G, pool, empty_fill)
 
 
+def _fuse_plain_dict(group_descriptors, group_weight):
+    """nets/model.py:94-100 on an arbitrary {index: tensor} dict: numerator = sum over the dict's entries of
+    group_weight[key] * value, denominator = sum of ALL group weights.  Runs the pooling kernel with every entry
+    as a one-member group (max of one value = the value), so the arithmetic is the fused path's:
+    acc += w_key * P_key in ascending key order (the reference's dict order for any dict view_pooling built),
+    one division.  Differentiable w.r.t. the entries."""
+    if len(group_descriptors) == 0:
+        raise ValueError("group_fusion: empty group_descriptors")
+    keys = sorted(group_descriptors.keys())
+    vals = [group_descriptors[k] for k in keys]
+    for v in vals:
+        _require_cuda(v, "group_descriptors")
+    dev = vals[0].device
+    w = _small_to_device(group_weight, dev, torch.float32, "group_weight")
+    if w.dim() != 1:
+        raise ValueError("group_fusion on a plain dict takes one weight per group ([G])")
+    G = int(w.shape[0])
+    if any((not isinstance(k, int)) or k < 0 or k >= G for k in keys):
+        raise IndexError("group_descriptors has a key outside range(len(group_weight)) = range(%d)" % G)
+    if len(keys) > C.MAX_VIEWS:
+        raise ValueError("at most %d group descriptors" % C.MAX_VIEWS)
+    bins = torch.tensor(keys, dtype=torch.int32, device=dev)[None]
+    S, _ = _run_pool_fuse(tuple(vals), "list", bins, w, G, "max", 0.0, False)
+    return S
+
+
 def group_fusion(group_descriptors, group_weight):
     """Shape descriptor = sum_g w_g * P_g / sum_g w_g.  Mirrors nets/model.py:77-102.
 
-    With the GroupDescriptors returned by ``view_pooling`` this runs the fused
+    With the (unedited) GroupDescriptors returned by ``view_pooling`` this runs the fused
     single-pass kernel over the original views (and is differentiable w.r.t.
     them).  ``group_weight`` is honoured as given ([G] or [B, G] float32), so
-    weights other than ``model.group_weight``'s 1 + count also work.
+    weights other than ``model.group_weight``'s 1 + count also work.  Any other
+    ``{index: tensor}`` mapping - the reference's documented argument ("dic {index: group_desc}") - is fused
+    entry by entry (``_fuse_plain_dict``).
     """
-    if not isinstance(group_descriptors, GroupDescriptors):
-        raise TypeError("group_fusion expects the GroupDescriptors returned by view_pooling")
+    if not isinstance(group_descriptors, GroupDescriptors) or group_descriptors._edited:
+        if not hasattr(group_descriptors, "keys"):
+            raise TypeError("group_fusion expects a {group index: descriptor} mapping")
+        return _fuse_plain_dict(group_descriptors, group_weight)
     gd = group_descriptors
-    group_weight = _small_to_device(group_weight, gd._bins.device, torch.float32, "group_weight")
-    S, _ = _PoolFuseFn.apply(gd._bins, group_weight, gd._G, gd._pool, gd._fill, gd._layout,
-                             len(gd._views), *gd._views)
+    tag = _tag_of(group_weight)
+    if tag is not None and tag.get("kind") == "weight" and tag["bins"] is gd._bins:
+        w = None       # model.group_weight of this very scheme: the kernel computes 1 + n_g itself
+    else:
+        w = _small_to_device(group_weight, gd._bins.device, torch.float32, "group_weight")
+    S, _ = _run_pool_fuse(gd._views, gd._layout, gd._bins, w, gd._G, gd._pool, gd._fill, False)
     return S
 
 
@@ -613,64 +770,78 @@ def basic_pool(final_view_descriptors, layout=None):
                      group_weight=w)
 
 
+def _fused_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, want_mask, status, variant):
+    """gvcnn_grouping_fusion_fwd: score + bin, then pool + fuse, chained on the device."""
+    L = C.lib()
+    if (rv.B, rv.V) != (fv.B, fv.V) or rv.dtype != fv.dtype:
+        raise ValueError("raw and final view descriptors must agree in batch, views and dtype")
+    dev = fv.device
+    Wc, bc = W.contiguous(), b.contiguous()
+    buf = torch.empty((4, fv.B, fv.V), dtype=torch.int32, device=dev)      # x, scores, bins, flags: one allocation
+    x, scores, bins, flags = buf[0].view(torch.float32), buf[1].view(torch.float32), buf[2], buf[3]
+    S = torch.empty((fv.B, fv.D), dtype=fv.dtype, device=dev)
+    mask = None
+    if want_mask and pool == "max":
+        mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        C.check(L.gvcnn_grouping_fusion_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(x), _ptr(scores), _ptr(bins),
+                                            _ptr(flags), _ptr(S), _ptr(mask), _ptr(status), fv.B, fv.V, rv.D, fv.D,
+                                            G, _pool_code(pool, variant), ctypes.c_float(empty_fill), rv.layout,
+                                            fv.layout, _dtype_code(fv.dtype), edge_ulps, int(clamp), _stream()),
+                "gvcnn_grouping_fusion_fwd")
+    return S, x, scores, bins, flags, mask
+
+
 class _FusedFwdFn(torch.autograd.Function):
     """Per-shape scores + bins + pooling + fusion through gvcnn_grouping_fusion_fwd (two launches chained
     with programmatic dependent launch, no host hop); backward = the pooling/fusion backward (dF only, as
     in the reference)."""
 
     @staticmethod
-    def forward(ctx, W, b, G, pool, empty_fill, f_layout, r_layout, n_r, edge_ulps, clamp, *tensors):
-        L = C.lib()
+    def forward(ctx, W, b, G, pool, empty_fill, f_layout, r_layout, n_r, edge_ulps, clamp, status, variant, *tensors):
         r_t, f_t = tensors[:n_r], tensors[n_r:]
         rv = _Views(list(r_t) if r_layout == "list" else r_t[0], None if r_layout == "list" else r_layout, "R")
         fv = _Views(list(f_t) if f_layout == "list" else f_t[0], None if f_layout == "list" else f_layout, "F")
-        if (rv.B, rv.V) != (fv.B, fv.V) or rv.dtype != fv.dtype:
-            raise ValueError("raw and final view descriptors must agree in batch, views and dtype")
-        dev = fv.device
-        Wc, bc = W.contiguous(), b.contiguous()
-        x = torch.empty((fv.B, fv.V), dtype=torch.float32, device=dev)
-        scores = torch.empty_like(x)
-        bins = torch.empty((fv.B, fv.V), dtype=torch.int32, device=dev)
-        flags = torch.empty_like(bins)
-        status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
-        S = torch.empty((fv.B, fv.D), dtype=fv.dtype, device=dev)
         need_grad = any(t.requires_grad for t in f_t)
-        mask = None
-        if need_grad and pool == "max":
-            mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            C.check(L.gvcnn_grouping_fusion_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(x), _ptr(scores), _ptr(bins),
-                                                _ptr(flags), _ptr(S), _ptr(mask), _ptr(status), fv.B, fv.V, rv.D, fv.D,
-                                                G, _POOL[pool], ctypes.c_float(empty_fill), rv.layout, fv.layout,
-                                                _dtype_code(fv.dtype), edge_ulps, int(clamp), _stream()),
-                    "gvcnn_grouping_fusion_fwd")
-        ctx.fv, ctx.G, ctx.pool, ctx.n_r = fv, G, pool, n_r
-        ctx.save_for_backward(bins, mask if mask is not None else torch.empty(0, device=dev))
-        ctx.mark_non_differentiable(x, scores, bins, flags, status)
-        return S.reshape(fv.view_shape), x, scores, bins, flags, status
+        S, x, scores, bins, flags, mask = _fused_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, need_grad,
+                                                     status, variant)
+        ctx.fv, ctx.G, ctx.pool, ctx.n_r, ctx.variant = fv, G, pool, n_r, variant
+        ctx.save_for_backward(bins, mask if mask is not None else torch.empty(0, device=S.device))
+        ctx.mark_non_differentiable(x, scores, bins, flags)
+        return S.reshape(fv.view_shape), x, scores, bins, flags
 
     @staticmethod
     def backward(ctx, dS, *_unused):
         bins, mask = ctx.saved_tensors
         mask = mask if mask.numel() else None
         fv = ctx.fv
-        if mask is not None:
-            # the forward clamps out-of-range bins for pooling; the saved bins may hold the raw value
-            bins = bins.clamp(0, ctx.G - 1)
-        out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins, fv.V if fv.B > 1 else 0, None, 0, mask, ctx.G, ctx.pool)
+        # bins may hold the raw out-of-range value (clamp=False); the backward kernel clamps like the forward did
+        out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins, fv.V if fv.B > 1 else 0, None, 0, mask, ctx.G, ctx.pool,
+                             ctx.variant)
         gf = tuple(out) if isinstance(out, list) else (out,)
-        return (None,) * 10 + (None,) * ctx.n_r + gf
+        return (None,) * 12 + (None,) * ctx.n_r + gf
 
 
 def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max",
-                    empty_fill=1.0, score_reduce="shape", layout=None, clamp=False, check=True,
-                    process_group=None, edge_ulps=1):
+                    empty_fill=1.0, score_reduce="shape", layout=None, clamp=False, check=False,
+                    process_group=None, edge_ulps=1, status=None, multiplier=None, exchange=None,
+                    global_count=None, _variant=0):
     """The whole hot path with no host hop (replaces the partial_run split of
     train.py:264-288): per-shape mode is one call into the library (score + bin,
     then pool + fuse, chained on the device); the literal batch-mean mode needs
     the cross-shape mean first and runs the stages separately.
-    Returns (shape_descriptor, ScoreResult)."""
+    Returns (shape_descriptor, ScoreResult).
+
+    check=True turns out-of-range / NaN scores into the reference's IndexError / ValueError right away (one
+    16-byte device->host read per call, i.e. a synchronisation); the default records nothing.  For a training
+    loop pass a persistent ``status`` tensor (int32[4], zeros) - the counters accumulate into it without any
+    synchronisation - and call ``raise_for_status(status, num_group)`` every N steps."""
+    if status is None and check:
+        dev0 = W.device if isinstance(W, torch.Tensor) else None
+        status = _new_status(dev0)
     if score_reduce == "shape":
+        if multiplier not in (None, num_group):
+            raise ValueError("multiplier is only selectable with score_reduce='batch' or through group_scheme")
         if isinstance(raw_view_descriptors, (list, tuple)):
             r_t, r_lay = tuple(raw_view_descriptors), "list"
         else:
@@ -682,15 +853,126 @@ def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_grou
         _require_cuda(W, "W"), _require_cuda(b, "b")
         if W.dtype != torch.float32 or b.dtype != torch.float32:
             raise TypeError("W and b must be float32")
-        S, x, scores, bins, flags, status = _FusedFwdFn.apply(W, b, num_group, pool, empty_fill, f_lay, r_lay,
-                                                              len(r_t), edge_ulps, clamp, *r_t, *f_t)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in f_t):
+            S, x, scores, bins, flags = _FusedFwdFn.apply(W, b, num_group, pool, empty_fill, f_lay, r_lay, len(r_t),
+                                                          edge_ulps, clamp, status, _variant, *r_t, *f_t)
+        else:
+            rv = _Views(list(r_t) if r_lay == "list" else r_t[0], None if r_lay == "list" else r_lay, "R")
+            fv = _Views(list(f_t) if f_lay == "list" else f_t[0], None if f_lay == "list" else f_lay, "F")
+            S, x, scores, bins, flags, _ = _fused_fwd(W, b, num_group, pool, empty_fill, rv, fv, edge_ulps, clamp,
+                                                      False, status, _variant)
+            S = S.reshape(fv.view_shape)
         sr = ScoreResult(x, scores, bins, flags, status, num_group)
         if check:
             sr.check()
         return S, sr
-    sr = score_bin(raw_view_descriptors, W, b, num_group, score_reduce=score_reduce, layout=layout,
-                   edge_ulps=edge_ulps, clamp=clamp, check=check, process_group=process_group)
-    S = pool_fuse(final_view_descriptors, sr.bins, num_group, pool=pool, empty_fill=empty_fill, layout=layout)
+    if score_reduce != "batch":
+        raise ValueError("score_reduce must be 'shape' or 'batch'")
+    return _grouping_fusion_batch(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool, empty_fill,
+                                  layout, clamp, check, process_group, edge_ulps, status, multiplier, exchange,
+                                  global_count, _variant)
+
+
+class _BatchFwdFn(torch.autograd.Function):
+    """Reference-literal forward (one scheme per batch) through gvcnn_grouping_fusion_batch_fwd; backward = the
+    pooling/fusion backward with the shared bin row."""
+
+    @staticmethod
+    def forward(ctx, W, b, G, pool, empty_fill, f_layout, r_layout, n_r, edge_ulps, clamp, status, variant, multiplier,
+                global_count, exchange_c, *tensors):
+        r_t, f_t = tensors[:n_r], tensors[n_r:]
+        rv = _Views(list(r_t) if r_layout == "list" else r_t[0], None if r_layout == "list" else r_layout, "R")
+        fv = _Views(list(f_t) if f_layout == "list" else f_t[0], None if f_layout == "list" else f_layout, "F")
+        need_grad = any(t.requires_grad for t in f_t)
+        S, xm, scores, bins, flags, mask = _batch_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, need_grad,
+                                                      status, variant, multiplier, global_count, exchange_c)
+        ctx.fv, ctx.G, ctx.pool, ctx.n_r, ctx.variant = fv, G, pool, n_r, variant
+        ctx.save_for_backward(bins, mask if mask is not None else torch.empty(0, device=S.device))
+        ctx.mark_non_differentiable(xm, scores, bins, flags)
+        return S.reshape(fv.view_shape), xm, scores, bins, flags
+
+    @staticmethod
+    def backward(ctx, dS, *_unused):
+        bins, mask = ctx.saved_tensors
+        mask = mask if mask.numel() else None
+        fv = ctx.fv
+        out = _pool_fuse_bwd(dS.reshape(fv.B, fv.D), fv, bins, 0, None, 0, mask, ctx.G, ctx.pool, ctx.variant)
+        gf = tuple(out) if isinstance(out, list) else (out,)
+        return (None,) * 15 + (None,) * ctx.n_r + gf
+
+
+def _batch_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, want_mask, status, variant, multiplier,
+               global_count, exchange_c):
+    L = C.lib()
+    if (rv.B, rv.V) != (fv.B, fv.V) or rv.dtype != fv.dtype:
+        raise ValueError("raw and final view descriptors must agree in batch, views and dtype")
+    dev = fv.device
+    Wc, bc = W.contiguous(), b.contiguous()
+    xb = torch.empty((max(fv.B, 1), fv.V), dtype=torch.float32, device=dev)
+    buf = torch.empty((5, 1, fv.V), dtype=torch.int32, device=dev)           # xsum, x_mean, scores, bins, flags
+    xsum, xm, scores = (buf[i].view(torch.float32) for i in range(3))
+    bins, flags = buf[3], buf[4]
+    S = torch.empty((fv.B, fv.D), dtype=fv.dtype, device=dev)
+    mask = None
+    if want_mask and pool == "max":
+        mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
+    fn, user = exchange_c if exchange_c is not None else (None, None)
+    with torch.cuda.device(dev):
+        C.check(L.gvcnn_grouping_fusion_batch_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(xb), _ptr(xsum), _ptr(xm),
+                                                  _ptr(scores), _ptr(bins), _ptr(flags), _ptr(S), _ptr(mask),
+                                                  _ptr(status), fv.B, fv.V, rv.D, fv.D, G, int(multiplier or 0),
+                                                  _pool_code(pool, variant), ctypes.c_float(empty_fill), rv.layout,
+                                                  fv.layout, _dtype_code(fv.dtype), edge_ulps, int(clamp),
+                                                  int(global_count), fn, user, _stream()),
+                "gvcnn_grouping_fusion_batch_fwd")
+    return S, xm, scores, bins, flags, mask
+
+
+def _grouping_fusion_batch(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool, empty_fill, layout,
+                           clamp, check, process_group, edge_ulps, status, multiplier, exchange, global_count, variant):
+    """score_reduce='batch': ONE call into the library (x -> column sums -> [exchange] -> mean -> one bin row ->
+    pool + fuse, PDL-chained).  `exchange`: a P2PComm.exchange_c pair, or None with `process_group` given, in which
+    case torch.distributed carries the V sums (called back from inside the library, in stream order)."""
+    if isinstance(raw_view_descriptors, (list, tuple)):
+        r_t, r_lay = tuple(raw_view_descriptors), "list"
+    else:
+        r_t, r_lay = (raw_view_descriptors,), (layout or "bvd")
+    if isinstance(final_view_descriptors, (list, tuple)):
+        f_t, f_lay = tuple(final_view_descriptors), "list"
+    else:
+        f_t, f_lay = (final_view_descriptors,), (layout or "bvd")
+    _require_cuda(W, "W"), _require_cuda(b, "b")
+    if W.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError("W and b must be float32")
+    B_local = r_t[0].shape[0] if r_lay in ("list", "bvd") else r_t[0].shape[1]
+    keep = None
+    exchange_c = exchange
+    if exchange_c is None and process_group is not None:
+        cb, keep = make_exchange(process_group)
+        exchange_c = (ctypes.cast(cb, ctypes.c_void_p), None)
+    if global_count is None:
+        global_count = B_local
+        if process_group is not None:
+            import torch.distributed as dist
+            cnt = torch.tensor([B_local], dtype=torch.int64, device=W.device)
+            dist.all_reduce(cnt, group=process_group)
+            global_count = int(cnt.item())
+    if global_count <= 0:
+        raise ValueError("score_reduce='batch' over an empty (global) batch")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in f_t):
+        S, xm, scores, bins, flags = _BatchFwdFn.apply(W, b, num_group, pool, empty_fill, f_lay, r_lay, len(r_t),
+                                                       edge_ulps, clamp, status, variant, multiplier, global_count,
+                                                       exchange_c, *r_t, *f_t)
+    else:
+        rv = _Views(list(r_t) if r_lay == "list" else r_t[0], None if r_lay == "list" else r_lay, "R")
+        fv = _Views(list(f_t) if f_lay == "list" else f_t[0], None if f_lay == "list" else f_lay, "F")
+        S, xm, scores, bins, flags, _ = _batch_fwd(W, b, num_group, pool, empty_fill, rv, fv, edge_ulps, clamp, False,
+                                                   status, variant, multiplier, global_count, exchange_c)
+        S = S.reshape(fv.view_shape)
+    del keep
+    sr = ScoreResult(xm, scores, bins, flags, status, num_group)
+    if check:
+        sr.check()
     return S, sr
 
 
@@ -800,7 +1082,8 @@ class GVCNNHead(torch.nn.Module):
         torch.nn.init.uniform_(self.classifier.weight, -lim2, lim2)
         torch.nn.init.zeros_(self.classifier.bias)
 
-    def forward(self, raw_view_descriptors, final_view_descriptors, process_group=None, check=True, fold_gap=False):
+    def forward(self, raw_view_descriptors, final_view_descriptors, process_group=None, check=False, fold_gap=False,
+                status=None, global_count=None):
         """raw: post-GAP block3 features [N, V, C_raw] (or list of V [N, C_raw]);
         final: list of V [N, h, w, C] maps or [N, V, h, w, C].  Returns
         (view_discrimination_scores, shape_descriptor, logits) like
@@ -809,7 +1092,8 @@ class GVCNNHead(torch.nn.Module):
         map is never written and the second return value is the pooled [N, C] descriptor."""
         if fold_gap and self.weight_mode == "count":
             sr = score_bin(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
-                           self.num_group, score_reduce=self.score_reduce, process_group=process_group, check=check)
+                           self.num_group, score_reduce=self.score_reduce, process_group=process_group, check=check,
+                           status=status, global_count=global_count)
             net = pool_fuse_gap(final_view_descriptors, sr.bins, self.num_group, pool=self.pool,
                                 empty_fill=self.empty_fill)
             return sr.scores, net, self.classifier(net.to(self.classifier.weight.dtype))
@@ -820,7 +1104,8 @@ class GVCNNHead(torch.nn.Module):
             S, sr = grouping_fusion(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
                                     final_view_descriptors, self.num_group, pool=self.pool,
                                     empty_fill=self.empty_fill, score_reduce=self.score_reduce,
-                                    process_group=process_group, check=check)
+                                    process_group=process_group, check=check, status=status,
+                                    global_count=global_count)
             scores = sr.scores
         net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
         logits = self.classifier(net.to(self.classifier.weight.dtype))

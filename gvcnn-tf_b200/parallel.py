@@ -11,11 +11,68 @@ forward needs no exchange in per-shape mode.  The only collectives are
   * init: broadcast of the head's parameters from rank 0
     (``utils/_train_helper.py:66-94``).
 Works with the ``nccl`` backend on GPUs and ``gloo`` on CPU (tests).
+
+Both exchanges are <= 50 KB and latency-bound; on the GPUs of one node they go through ``P2PComm``, the library's
+one-kernel all-reduce over NVLink peer memory (``csrc/comm.cu``), with torch.distributed only carrying the 64-byte
+IPC handles at start-up.  ``torch.distributed`` collectives remain the checked alternative (CPU tests, multi-node).
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+
+class P2PComm:
+    """gvcnn_comm (include/gvcnn_b200.h): one-shot all-reduce of small float32 vectors between the GPUs of one
+    node - push to every peer's receive buffer over NVLink, flag, wait, add in rank order (bit-identical on every
+    rank).  One process per GPU; ``group`` is only used to all-gather the IPC handles."""
+
+    def __init__(self, group=None, device=None):
+        from . import _cabi as C
+        self._C = C
+        self._L = C.lib()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > C.COMM_MAX_WORLD:
+            raise ValueError("P2PComm: at most %d ranks (one node)" % C.COMM_MAX_WORLD)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * C.COMM_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            C.check(self._L.gvcnn_comm_create(ctypes.byref(self._h), self.rank, self.world, handle), "gvcnn_comm_create")
+            mine = torch.tensor(list(handle), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                mine = mine.to(self.device)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=group)
+            blob = bytes(torch.cat([t.cpu() for t in allh]).tolist())
+            C.check(self._L.gvcnn_comm_connect(self._h, blob), "gvcnn_comm_connect")
+        dist.barrier(group)                                          # every rank has mapped every peer's buffer
+        # (function, user pointer) in the gvcnn_exchange_fn form the library's entry points take
+        self.exchange = (self._L.gvcnn_comm_allreduce_f32, self._h)
+        self.exchange_c = (ctypes.cast(self._L.gvcnn_comm_allreduce_f32, ctypes.c_void_p), self._h)
+
+    def all_reduce_(self, t: torch.Tensor, scale: float = 1.0, stream=None):
+        """In place: t = (sum over ranks of t) * scale; float32, contiguous, <= COMM_MAX_FLOATS elements,
+        ordered on ``stream`` (default: the current stream).  scale = 1 / world is the gradient average."""
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise TypeError("P2PComm.all_reduce_: contiguous float32 CUDA tensor expected")
+        st = torch.cuda.current_stream(t.device) if stream is None else stream
+        self._C.check(self._L.gvcnn_comm_allreduce_scaled_f32(self._h, ctypes.c_void_p(t.data_ptr()), t.numel(),
+                                                              ctypes.c_float(scale), ctypes.c_void_p(st.cuda_stream)),
+                      "gvcnn_comm_allreduce_scaled_f32")
+        return t
+
+    def check(self):
+        """Raises if a wait timed out (a peer never arrived).  Synchronises."""
+        self._C.check(self._L.gvcnn_comm_error(self._h), "gvcnn_comm_error")
+
+    def close(self):
+        if self._h:
+            self._L.gvcnn_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
 
 
 def shard_range(num_shapes: int, rank: int, world_size: int):
@@ -26,6 +83,24 @@ def shard_range(num_shapes: int, rank: int, world_size: int):
     base, rem = divmod(num_shapes, world_size)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def steps_per_epoch(num_shapes: int, world_size: int, batch_size: int) -> int:
+    """Steps every rank runs per epoch: the step count of the largest shard.  Shard sizes differ by up to one
+    shape, so ceil(shard / batch_size) can differ across ranks; ranks must still issue the same number of
+    collectives, so the short ones finish the epoch on empty batches."""
+    return max(-(-(shard_range(num_shapes, r, world_size)[1] - shard_range(num_shapes, r, world_size)[0]) // batch_size)
+               for r in range(world_size))
+
+
+def global_batch_size(num_shapes: int, world_size: int, batch_size: int, step: int) -> int:
+    """Number of shapes all ranks together process at `step` of an epoch (the divisor of the literal batch mean,
+    nets/model.py:146, on a sharded batch) - computable locally, no exchange needed."""
+    total = 0
+    for r in range(world_size):
+        lo, hi = shard_range(num_shapes, r, world_size)
+        total += max(0, min(batch_size, hi - (lo + step * batch_size)))
+    return total
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):

@@ -231,8 +231,13 @@ def write_feature_shard(prefix: str, raw: np.ndarray, final: np.ndarray, labels:
 
 
 class FeatureShard:
-    """Memory-mapped shard; ``batches`` stages consecutive shapes through two reused pinned buffers so the
-    host->device copies of ``gvcnn_grouping_fusion_host`` (or ``.cuda(non_blocking=True)``) run at PCIe rate."""
+    """Memory-mapped shard; ``batches`` stages consecutive shapes through a small ring of reused pinned buffers so
+    the host->device copies of ``gvcnn_grouping_fusion_host`` (or ``.cuda(non_blocking=True)``) run at PCIe rate.
+
+    Buffer reuse is ordered against the consumer's copies: before buffer k is refilled, the generator waits on the
+    CUDA event recorded (on the consumer's current stream) when the consumer came back for the next batch - i.e.
+    after it queued its ``.cuda(non_blocking=True)`` copy of the batch that lives in buffer k.  A loop that never
+    synchronises can therefore not have a pending async H2D read overwritten."""
 
     def __init__(self, prefix: str):
         self.raw = np.load(prefix + ".raw.npy", mmap_mode="r")
@@ -244,18 +249,27 @@ class FeatureShard:
     def __len__(self):
         return int(self.raw.shape[0])
 
-    def batches(self, batch_size: int, pin: bool = True, lo: int = 0, hi: int = None):
+    def batches(self, batch_size: int, pin: bool = True, lo: int = 0, hi: int = None, depth: int = 3):
         import torch
         hi = len(self) if hi is None else hi
         pin = pin and torch.cuda.is_available()
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
         rt = torch.from_numpy(np.zeros(0, self.raw.dtype)).dtype
         ft = torch.from_numpy(np.zeros(0, self.final.dtype)).dtype
+        depth = max(2, depth)
         bufs = [(mk((batch_size,) + self.raw.shape[1:], rt), mk((batch_size,) + self.final.shape[1:], ft))
-                for _ in range(2)]
+                for _ in range(depth)]
+        events = [None] * depth                                      # consumer-side "copies of this buffer are queued"
         for n, i in enumerate(range(lo, hi, batch_size)):
             j = min(i + batch_size, hi)
-            r, f = bufs[n & 1]
+            k = n % depth
+            if events[k] is not None:
+                events[k].synchronize()                              # the H2D copies that read buffer k have finished
+            r, f = bufs[k]
             r[:j - i].copy_(torch.from_numpy(np.array(self.raw[i:j])))
             f[:j - i].copy_(torch.from_numpy(np.array(self.final[i:j])))
             yield r[:j - i], f[:j - i], torch.from_numpy(np.asarray(self.labels[i:j]).copy())
+            if pin:                                                  # back from the consumer: its copies are queued
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                events[k] = ev

@@ -26,7 +26,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gvcnn_tf_b200 import model, parallel  # noqa: E402
+from gvcnn_tf_b200 import _cabi, model, parallel  # noqa: E402
+
+C_COMM_MAX_FLOATS, C_COMM_MAX_WORLD = _cabi.COMM_MAX_FLOATS, _cabi.COMM_MAX_WORLD
 
 
 def build_flags():
@@ -92,6 +94,10 @@ class SyntheticFeatures:
             j = min(i + bs, hi)
             yield (self.raw[i:j].to(self.device), self.final[i:j].to(self.device), self.labels[i:j].to(self.device))
 
+    def empty_batch(self):
+        """A zero-shape batch: what a rank whose shard is exhausted contributes to the epoch's last step."""
+        return (self.raw[:0].to(self.device), self.final[:0].to(self.device), self.labels[:0].to(self.device))
+
 
 def confusion_matrix(labels, preds, n):
     cm = torch.zeros((n, n), dtype=torch.int64)
@@ -125,6 +131,22 @@ def main(argv=None):
         parallel.broadcast_parameters(head, src=0)
     opt = torch.optim.SGD(head.parameters(), lr=flags.base_learning_rate, momentum=flags.momentum)
     bucket = parallel.GradBucket(list(head.parameters()), device=device) if world > 1 else None
+    comm, pg = None, None
+    if world > 1:
+        import torch.distributed as dist
+        pg = dist.group.WORLD
+        if bucket.flat.numel() <= C_COMM_MAX_FLOATS and world <= C_COMM_MAX_WORLD:
+            try:                                    # the library's one-kernel NVLink all-reduce (csrc/comm.cu)
+                comm = parallel.P2PComm()
+            except Exception as e:                  # noqa: BLE001 - e.g. IPC not permitted: NCCL carries the bucket
+                comm = None
+                if rank == 0:
+                    print("P2PComm unavailable (%s); gradient bucket goes through NCCL" % e)
+            ok = torch.tensor([1 if comm is not None else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and comm is not None:
+                comm.close()
+                comm = None
 
     start_epoch, global_step = 0, 0
     if flags.saved_checkpoint_dir:                  # train.py:229-234: restore the latest checkpoint
@@ -138,32 +160,52 @@ def main(argv=None):
     train = SyntheticFeatures(flags.train_size, flags, num_classes, flags.seed + 1, device)
     val = SyntheticFeatures(flags.val_size, flags, num_classes, flags.seed + 2, device)
     lo, hi = parallel.shard_range(flags.train_size, rank, world)
+    # every rank must issue the SAME number of collectives per epoch: shard sizes differ by up to one shape, so the
+    # step count is the largest rank's; a rank that has run out of shapes keeps stepping on an empty batch (zero
+    # gradients into the all-reduce, zero shapes into the global batch mean)
+    steps_per_epoch = parallel.steps_per_epoch(flags.train_size, world, flags.batch_size)
+    status = torch.zeros(4, dtype=torch.int32, device=device)       # out-of-range / NaN score counters, read once per epoch
     history = []
+    lr = learning_rate(flags, global_step)
     for epoch in range(start_epoch, flags.how_many_training_epochs):
         head.train()
         tot_loss, n_seen = 0.0, 0
-        for raw, final, y in train.batches(flags.batch_size, lo, hi):
+        it = iter(train.batches(flags.batch_size, lo, hi))
+        for _step in range(steps_per_epoch):
+            batch = next(it, None)
+            if batch is None:
+                batch = train.empty_batch()
+            raw, final, y = batch
             lr = learning_rate(flags, global_step)
             for gparam in opt.param_groups:
                 gparam["lr"] = lr
-            _, _, logits = head(raw, final)
-            loss = torch.nn.functional.cross_entropy(logits, y)
             opt.zero_grad(set_to_none=True)
-            loss.backward()
+            if len(y) > 0 or (world > 1 and flags.score_reduce == "batch"):
+                # literal mode on a sharded batch: every rank bins the same GLOBAL batch mean
+                _, _, logits = head(raw, final, process_group=pg if flags.score_reduce == "batch" else None,
+                                    status=status,
+                                    global_count=parallel.global_batch_size(flags.train_size, world, flags.batch_size, _step))
+            if len(y) > 0:
+                loss = torch.nn.functional.cross_entropy(logits, y)
+                loss.backward()
+                tot_loss += float(loss.detach()) * len(y)
+                n_seen += len(y)
             if bucket is not None:                  # one flat all-reduce (utils/_train_helper.py:17-31)
                 bucket.pack()
-                bucket.all_reduce_mean()
+                if comm is not None:
+                    comm.all_reduce_(bucket.flat, 1.0 / world)      # sum * 1/K, one kernel, stream ordered
+                else:
+                    bucket.finish(bucket.all_reduce_mean(async_op=True))
                 bucket.unpack()
             opt.step()
             global_step += 1
-            tot_loss += float(loss.detach()) * len(y)
-            n_seen += len(y)
+        model.raise_for_status(status, flags.num_group)             # the reference's IndexError / ValueError, once per epoch
         # validation (train.py:319-374)
         head.eval()
         correct, cm = 0, torch.zeros((num_classes, num_classes), dtype=torch.int64)
         with torch.no_grad():
             for raw, final, y in val.batches(flags.val_batch_size):
-                _, _, logits = head(raw, final)
+                _, _, logits = head(raw, final)        # validation runs un-sharded on every rank: local batch mean
                 pred = logits.argmax(dim=1)
                 correct += int((pred == y).sum())
                 cm += confusion_matrix(y.cpu(), pred.cpu(), num_classes)

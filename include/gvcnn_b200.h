@@ -9,8 +9,11 @@
  *
  * Conventions (all entry points):
  *   - every tensor pointer is a DEVICE pointer owned by the caller unless the
- *     name says `host`; the library allocates nothing persistent and keeps no
- *     global state; calls are stream-ordered, asynchronous and re-entrant;
+ *     name says `host`; the library keeps no mutable global state and allocates
+ *     no device memory of its own (the only objects with a lifetime are the
+ *     explicit gvcnn_host_pipeline / gvcnn_comm handles the caller creates and
+ *     destroys; a gvcnn_comm owns its 1 MB peer-visible receive buffer);
+ *     calls are stream-ordered, asynchronous and re-entrant;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - return value: 0 = ok, < 0 = GVCNN_E_* argument error (nothing was
  *     launched), > 0 = a cudaError_t from the launch;  nothing throws;
@@ -33,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GVCNN_ABI_VERSION 1
+#define GVCNN_ABI_VERSION 2
 #define GVCNN_MAX_VIEWS 128      /* V: 6..80 in the reference's sweeps           */
 #define GVCNN_MAX_GROUPS 4096    /* num_group; the reference only ever uses 10   */
 
@@ -54,6 +57,18 @@ extern "C" {
 
 #define GVCNN_POOL_MAX 0         /* tf.reduce_max, nets/model.py:72 (shipped)    */
 #define GVCNN_POOL_MEAN 1        /* tf.reduce_mean, unit_test.py:31              */
+/* A/B measurement and tests only: bits 8..11 of a `pool` argument pick the forward
+ * (and the matching backward) pooling kernel - 0 = auto (3 when it applies, else 1,
+ * else 2), 1 = one tile per CTA, bulk-copy (TMA, cp.async.bulk) staged, 2 = one tile
+ * per CTA, plain vector loads staged through shared memory, 3 = persistent
+ * warp-specialised TMA ring.  Stateless: the choice travels with the call. */
+#define GVCNN_POOL_VARIANT(v) ((v) << 8)
+#define GVCNN_POOL_VARIANT_OF(pool) (((pool) >> 8) & 0xf)
+
+/* score granularity */
+#define GVCNN_SCORE_REDUCE_SHAPE 0 /* one score per (shape, view): bins [B, V]         */
+#define GVCNN_SCORE_REDUCE_BATCH 1 /* tf.reduce_mean over the batch, nets/model.py:146:
+                                      one [V] scheme shared by the batch (the reference) */
 
 /* status words */
 #define GVCNN_STATUS_WORDS 4
@@ -78,6 +93,7 @@ extern "C" {
 #define GVCNN_E_BAD_MODE (-8)
 #define GVCNN_E_WORKSPACE (-9)   /* workspace too small                          */
 #define GVCNN_E_UNSUPPORTED (-10) /* specialised entry point: shapes not covered */
+#define GVCNN_E_COMM_TIMEOUT (-11) /* gvcnn_comm: a peer never arrived             */
 
 int gvcnn_version(void);
 const char *gvcnn_strerror(int code);
@@ -107,11 +123,16 @@ int gvcnn_batch_sum_x(const float *x, float *xsum, int B, int V, void *stream);
  *   bin = (int)(s * (float)G) float32 multiply, truncation; nets/model.py:23
  * Replaces model.group_scheme (nets/model.py:16-25; train.py:277) - the
  * one-hot [G, V] scheme is the dense form of `bins`.
+ * multiplier: 0 = G (the generalisation used by the fused kernels, identical to
+ * the reference at num_group == 10); > 0 = that literal value - 10 reproduces the
+ * hard-coded `score * 10` of nets/model.py:23 for any num_group (a bin >= G is
+ * then the reference's IndexError, reported through flags / status).
+ * x_mean (nullable) receives xm.
  * flags (nullable) gets GVCNN_FLAG_* per element; status counts them.
  * clamp != 0 stores min(bin, G-1) instead of the out-of-range value (the
  * flag / status are still raised). */
-int gvcnn_score_bin(const float *x, float denom, float *scores, int32_t *bins,
-                    int32_t *flags, int32_t *status, int64_t n, int G,
+int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins,
+                    int32_t *flags, int32_t *status, int64_t n, int G, int multiplier,
                     int edge_ulps, int clamp, void *stream);
 
 /* gvcnn_view_score_fwd + gvcnn_score_bin(denom = 1) in ONE kernel: the
@@ -124,8 +145,8 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias,
 
 /* --- scheme / weight glue (the reference's host NumPy part) -----------------
  * gvcnn_bins_from_scores: model.group_scheme's arithmetic on already-computed
- *   scores (nets/model.py:23): bin = (int)(float32(s) * float32(G)); same
- *   flags / status / clamp behaviour as gvcnn_score_bin.
+ *   scores (nets/model.py:23): bin = (int)(float32(s) * float32(multiplier or G));
+ *   same multiplier / flags / status / clamp behaviour as gvcnn_score_bin.
  * gvcnn_bins_to_scheme: dense one-hot int32 [rows, G, V] exactly as
  *   model.group_scheme returns it (nets/model.py:21-23) from bins [rows, V].
  * gvcnn_scheme_to_bins: the inverse, for callers that hand view_pooling a
@@ -135,7 +156,7 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias,
  * gvcnn_group_weight: model.group_weight (nets/model.py:28-41):
  *   weights[row, g] = 1 + #{v : bins[row, v] == g}, float32 [rows, G]. */
 int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, int32_t *status,
-                           int64_t n, int G, int edge_ulps, int clamp, void *stream);
+                           int64_t n, int G, int multiplier, int edge_ulps, int clamp, void *stream);
 int gvcnn_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, void *stream);
 int gvcnn_scheme_to_bins(const int32_t *scheme, int32_t *bins, int32_t *status, int rows, int V, int G,
                          void *stream);
@@ -192,6 +213,26 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
                               int r_layout, int f_layout, int dtype, int edge_ulps, int clamp,
                               void *stream);
 
+/* --- the whole forward, reference-literal (one scheme per batch) -----------
+ * nets/model.py:144-157 as train.py:264-288 drives it, without the host hop:
+ *   x[b, v] (gvcnn_view_score_fwd) -> xsum[v] = sum_b x[b, v] (gvcnn_batch_sum_x)
+ *   -> [exchange: all-reduce(sum) of xsum across ranks, in stream order]
+ *   -> xm = xsum / global_count = tf.reduce_mean(raw) (nets/model.py:146),
+ *      s = sigmoid(log|xm|), bin = (int)(s * (multiplier or G)) - ONE [V] row
+ *   -> pool + fuse of every shape with that row (bin stride 0).
+ * x [B, V], xsum [V], scores / bins / flags (nullable) [V], x_mean (nullable) [V].
+ * global_count: the number of shapes the mean is over (B, or the sum over the
+ * ranks of a sharded batch).  exchange (nullable) as in gvcnn_grouping_fusion_host.
+ * All launches are chained with programmatic dependent launch. */
+typedef int (*gvcnn_exchange_fn)(void *user, float *xsum_dev, int n, void *stream);
+int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *bias, const void *F,
+                                    float *x, float *xsum, float *x_mean, float *scores, int32_t *bins,
+                                    int32_t *flags, void *S, uint8_t *tie_mask, int32_t *status,
+                                    int B, int V, int C, int64_t D, int G, int multiplier,
+                                    int pool, float empty_fill, int r_layout, int f_layout, int dtype,
+                                    int edge_ulps, int clamp, int64_t global_count,
+                                    gvcnn_exchange_fn exchange, void *exchange_user, void *stream);
+
 /* --- pooling + fusion with the following global average pooling folded in ---
  * nets/model.py:154-163: view_pooling -> group_fusion -> GlobalAveragePooling2D.
  * The descriptors are channel-last maps, D = HW * C per view (nets/model.py:149:
@@ -245,31 +286,76 @@ int gvcnn_view_score_bwd(const void *R, const float *dx, const float *W, float *
                          void *dR, void *workspace, size_t workspace_bytes,
                          int B, int V, int C, int r_layout, int dtype, void *stream);
 
-/* Which forward pooling kernel the next calls use: 0 = auto (3 when it applies,
- * else 1, else 2), 1 = one tile per CTA, bulk-copy (TMA, cp.async.bulk) staged,
- * 2 = one tile per CTA, plain vector loads staged through shared memory,
- * 3 = persistent warp-specialised TMA ring.  Process-wide, for A/B measurement
- * and tests only. */
-int gvcnn_set_pool_variant(int variant);
-
 /* --- host-buffer path (end-to-end) ---------------------------------------
  * One call = what one `sess.partial_run` pair does for this path in
- * train.py:270-288, with HOST (preferably pinned) buffers: copies R and F to
- * the device in chunks of shapes, runs score+bin and pool+fuse, copies S (and
- * scores / bins if non-null) back, overlapping copies with kernels on two
- * streams.  BVD layout.  d_workspace is caller-owned device memory of at
- * least gvcnn_host_workspace_bytes(...) bytes.  Synchronous: returns when the
+ * train.py:264-288, with HOST (preferably pinned) buffers: copies R and F to
+ * the device in chunks of `chunk_shapes` shapes, runs score+bin and pool+fuse,
+ * copies S (and scores / bins if non-null) back, overlapping copy-in, kernels
+ * and copy-out on separate streams.  BVD layout.  Synchronous: returns when the
  * outputs are in host memory.  If dS_host / dF_host are non-null it also runs
- * the backward and returns dF. */
-size_t gvcnn_host_workspace_bytes(int chunk_shapes, int V, int C, int64_t D, int dtype, int training);
-int gvcnn_grouping_fusion_host(const void *R_host, const void *F_host,
+ * the backward and returns dF.
+ *   pipe: streams + events, created once with gvcnn_host_pipeline_create
+ *     (h2d_streams = 1 or 2 copy-in streams) on the device it will be used on.
+ *   score_reduce = GVCNN_SCORE_REDUCE_SHAPE: scores_host / bins_host are [B, V].
+ *   score_reduce = GVCNN_SCORE_REDUCE_BATCH (the reference's only mode,
+ *     nets/model.py:146): two passes over the host data - R -> x [B, V] -> column
+ *     sums -> mean -> ONE scores / bins row ([V]; scores_host / bins_host get V
+ *     values) -> F -> S; the copies of F are queued behind those of R without
+ *     waiting for the bins.  global_count = the number of shapes the mean is
+ *     taken over (B on one GPU; the sum over ranks when the batch is sharded).
+ *     exchange (nullable): called once, after the local column sums are queued
+ *     on `stream`; must all-reduce(sum) xsum_dev[0..n) in place across the
+ *     ranks IN STREAM ORDER on `stream` and return 0 (SURVEY.md 8e collective
+ *     (2)); gvcnn_comm_allreduce_f32 has this signature with user = the comm.
+ * d_workspace: caller-owned device memory of gvcnn_host_workspace_bytes(...). */
+typedef struct gvcnn_host_pipeline gvcnn_host_pipeline;
+int gvcnn_host_pipeline_create(gvcnn_host_pipeline **out, int h2d_streams);
+int gvcnn_host_pipeline_destroy(gvcnn_host_pipeline *pipe);
+size_t gvcnn_host_workspace_bytes(int B, int chunk_shapes, int V, int C, int64_t D, int dtype,
+                                  int training, int score_reduce);
+int gvcnn_grouping_fusion_host(gvcnn_host_pipeline *pipe,
+                               const void *R_host, const void *F_host,
                                const float *W_dev, const float *bias_dev,
                                void *S_host, float *scores_host, int32_t *bins_host,
                                const void *dS_host, void *dF_host,
                                int32_t *status_host,
                                int B, int V, int C, int64_t D, int G, int pool, float empty_fill,
-                               int dtype, int chunk_shapes,
-                               void *d_workspace, size_t workspace_bytes);
+                               int dtype, int score_reduce, int64_t global_count,
+                               gvcnn_exchange_fn exchange, void *exchange_user,
+                               int chunk_shapes, void *d_workspace, size_t workspace_bytes);
+
+/* --- one-shot all-reduce over NVLink peer memory ----------------------------
+ * The B200-native form of the reference's only collective, `nccl_ops.all_sum`
+ * + `* 1/K` per gradient (utils/_train_helper.py:17-31), for the two exchanges of
+ * this path: the flat parameter-gradient bucket (V * (C_raw + 1)
+ * floats) and the V partial sums of the literal batch mean.  One process per
+ * GPU, up to GVCNN_COMM_MAX_WORLD GPUs of one node, vectors of up to
+ * GVCNN_COMM_MAX_FLOATS floats.  One kernel per rank: push to every peer's
+ * receive buffer (cudaIpc-mapped, NVLink stores), flag, wait, add the K slots
+ * in rank order (bit-identical result on every rank), scale, in place; no host
+ * rendezvous, graph-capturable.
+ *   gvcnn_comm_create: allocates this rank's receive buffer on the current
+ *     device and writes its GVCNN_COMM_HANDLE_BYTES-byte IPC handle to
+ *     handle_out; the caller all-gathers the handles by any means (the Python
+ *     mirror uses torch.distributed) and passes the K handles, rank-major, to
+ *   gvcnn_comm_connect.
+ *   gvcnn_comm_allreduce_f32(comm, data, n, stream): sum, in place, stream
+ *     ordered; has the gvcnn_exchange_fn signature (user = the comm).
+ *   gvcnn_comm_allreduce_scaled_f32: (sum) * scale - scale = 1/K is the
+ *     reference's gradient average.
+ *   gvcnn_comm_error: 0, or GVCNN_E_COMM_TIMEOUT if a wait gave up (a peer did
+ *     not arrive within 4 s); synchronises.
+ * Every rank must issue the same sequence of calls with the same n. */
+#define GVCNN_COMM_MAX_WORLD 8
+#define GVCNN_COMM_MAX_FLOATS 16384
+#define GVCNN_COMM_HANDLE_BYTES 64
+typedef struct gvcnn_comm gvcnn_comm;
+int gvcnn_comm_create(gvcnn_comm **out, int rank, int world, void *handle_out);
+int gvcnn_comm_connect(gvcnn_comm *comm, const void *all_handles);
+int gvcnn_comm_allreduce_f32(void *comm, float *data_dev, int n, void *stream);
+int gvcnn_comm_allreduce_scaled_f32(void *comm, float *data_dev, int n, float scale, void *stream);
+int gvcnn_comm_error(gvcnn_comm *comm);
+int gvcnn_comm_destroy(gvcnn_comm *comm);
 
 #ifdef __cplusplus
 }

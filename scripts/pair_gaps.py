@@ -25,9 +25,7 @@ K = {
     "B": lambda i: C.check(L.gvcnn_pool_fuse_bwd(p(dSs[i % nset]), p(bins), V, None, 0, p(mask), p(dF), p(status), B, V, D, G, 0, 0, 0, sp), "b"),
 }
 def generic_pool(i, with_mask):   # the one-tile-per-CTA kernel (variant 1) instead of the persistent ring
-    L.gvcnn_set_pool_variant(1)
-    C.check(L.gvcnn_pool_fuse_fwd(p(Fs[i % nset]), p(bins), V, None, 0, p(S), None, p(mask) if with_mask else None, p(status), B, V, D, G, 0, one, 0, 0, sp), "q")
-    L.gvcnn_set_pool_variant(0)
+    C.check(L.gvcnn_pool_fuse_fwd(p(Fs[i % nset]), p(bins), V, None, 0, p(S), None, p(mask) if with_mask else None, p(status), B, V, D, G, C.pool_variant(0, 1), one, 0, 0, sp), "q")
 K["q"] = lambda i: generic_pool(i, False)
 K["Q"] = lambda i: generic_pool(i, True)
 K["S"](0); torch.cuda.synchronize()

@@ -23,6 +23,12 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["vs_baseline"] is None
+    # like for like: the FULL configs[1] batch every step, and the very config object the CUDA arm prints
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.bench_config(1, "weak") and line["config"]["B_per_gpu"] == 4096
+    assert line["config"]["score_reduce"] == "batch"
+    assert abs(line["value"] - 4096 / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -36,7 +36,7 @@ def test_header_symbols_are_exported_and_bound(cabi):
         assert hasattr(L, s), "declared in include/gvcnn_b200.h but not exported: " + s
         assert s in cabi.SIGNATURES, "exported but not bound in _cabi.py: " + s
     assert sorted(cabi.SIGNATURES) == syms
-    assert L.gvcnn_version() == 1
+    assert L.gvcnn_version() == 2
     assert b"ok" == L.gvcnn_strerror(0)
     for code in range(-9, 0):
         assert b"unknown" not in L.gvcnn_strerror(code)
@@ -73,9 +73,18 @@ def test_argument_errors_before_any_launch(cabi):
     odd = ctypes.c_void_p(p.value + 2)
     assert L.gvcnn_pool_fuse_fwd(odd, p, 12, None, 0, p, None, None, None, 4, 12, 64, 8, 0, 1.0, 0, 0, None) == -6
     assert L.gvcnn_score_bin_fwd(p, None, p, None, p, p, None, None, 4, 12, 64, 8, 0, 0, 1, 0, None) == -1
-    assert L.gvcnn_set_pool_variant(7) == -8 and L.gvcnn_set_pool_variant(0) == 0
-    assert L.gvcnn_host_workspace_bytes(256, 12, 1024, 2048, 0, 0) > 256 * 12 * 2048 * 4 * 3
-    assert L.gvcnn_host_workspace_bytes(0, 12, 1024, 2048, 0, 0) == 0
+    # the A/B kernel-variant selector rides in bits 8..11 of `pool` (stateless); values above 3 are rejected
+    assert L.gvcnn_pool_fuse_fwd(p, p, 12, None, 0, p, None, None, None, 4, 12, 64, 8, cabi.pool_variant(0, 7), 1.0, 0, 0, None) == -8
+    assert L.gvcnn_host_workspace_bytes(4096, 256, 12, 1024, 2048, 0, 0, 0) > 256 * 12 * 2048 * 4 * 3
+    assert (L.gvcnn_host_workspace_bytes(4096, 256, 12, 1024, 2048, 0, 0, 1)
+            >= L.gvcnn_host_workspace_bytes(4096, 256, 12, 1024, 2048, 0, 0, 0) + 4096 * 12 * 4)
+    assert L.gvcnn_host_workspace_bytes(4096, 0, 12, 1024, 2048, 0, 0, 0) == 0
+    # the host entry point needs a pipeline object and validates its modes before touching the device
+    assert L.gvcnn_grouping_fusion_host(None, p, p, p, p, p, None, None, None, None, None, 4, 12, 64, 64, 8, 0, 1.0,
+                                        0, 0, 4, None, None, 2, p, 1 << 20) == -1
+    assert L.gvcnn_grouping_fusion_host(None, p, p, p, p, p, None, None, None, None, None, 4, 12, 64, 64, 8, 0, 1.0,
+                                        0, 5, 4, None, None, 2, p, 1 << 20) == -8
+    assert L.gvcnn_score_bin(p, 1.0, None, p, p, None, None, 12, 8, -1, 0, 0, None) == -1      # negative multiplier
     if not torch.cuda.is_available():
         assert L.gvcnn_check_device() == -7            # no CPU fallback: the library says so
 
@@ -90,8 +99,10 @@ def test_python_mirror_has_no_cpu_path():
         model.score_bin(torch.zeros(2, 3, 8), torch.zeros(3, 8), torch.zeros(3), 4)
     with pytest.raises(RuntimeError, match="no CPU path"):
         model.view_pooling([torch.zeros(2, 8)] * 3, torch.zeros(4, 3, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.group_fusion({0: torch.zeros(2)}, torch.ones(1))        # a plain dict is accepted, CPU tensors are not
     with pytest.raises(TypeError):
-        model.group_fusion({0: torch.zeros(2)}, torch.ones(1))
+        model.group_fusion([torch.zeros(2)], torch.ones(1))
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -105,12 +105,138 @@ def test_reference_error_behaviour(model):
     b = dev(np.zeros(2, dtype=np.float32))
     with pytest.raises(IndexError):
         model.score_bin(R, W, b, 10)
-    sr = model.score_bin(R, W, b, 10, clamp=True, check=False)
+    st = torch.zeros(4, dtype=torch.int32, device="cuda")        # a persistent status tensor: counters accumulate, no sync
+    sr = model.score_bin(R, W, b, 10, clamp=True, check=False, status=st)
     assert sr.bins.cpu().tolist() == [[9, 9]] and int(sr.status[0]) == 2
+    model.score_bin(R, W, b, 10, clamp=True, check=False, status=st)
+    assert int(st[0]) == 4
+    with pytest.raises(IndexError):
+        model.raise_for_status(st, 10)
+    assert model.score_bin(R, W, b, 10, clamp=True, check=False).status is None
     Rn = R.clone()
     Rn[0, 0, 0] = float("nan")
     with pytest.raises(ValueError):
         model.score_bin(Rn, W, b, 10)
+
+
+# ---------------------------------------------------------------- the reference-shaped call sequence
+@pytest.mark.parametrize("V,D,G", [(12, 2048, 8), (6, 1024, 10), (20, 2048, 16), (10, 512, 10), (12, 2048, 70)])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0), ("mean", 1.0)])
+def test_group_fusion_custom_weights_with_empty_fill(model, V, D, G, pool, fill):
+    """group_fusion(view_pooling(views, scheme), w) with caller weights that are NOT 1 + n_g and the ones dummy for
+    empty groups (nets/model.py:63,94-100: an empty group contributes w_g * 1): the persistent ring kernel's
+    weights instantiation, the one-tile generic kernel and the oracle's literal graph agree bit for bit."""
+    B = 37
+    rng = np.random.default_rng(V * D + G)
+    F = np.maximum(rng.standard_normal((B, V, D)), -0.3).astype(np.float32)
+    brow = rng.integers(0, G, V).astype(np.int32)
+    brow[: V // 2] = brow[0]                                 # a big group, several empty ones
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[brow, np.arange(V)] = 1
+    w = rng.uniform(0.25, 3.0, G).astype(np.float32)
+    views_np = [F[:, v, :] for v in range(V)]
+    want = O.group_fusion(O.view_pooling(views_np, scheme, pool=pool, empty_fill=fill), w)
+    views = [dev(a) for a in views_np]
+    got = model.group_fusion(model.view_pooling(views, dev(scheme), pool=pool, empty_fill=fill), dev(w))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    for variant in (1, 3):
+        S = model.pool_fuse(views, dev(brow), G, pool=pool, empty_fill=fill, group_weight=dev(w), _variant=variant)
+        np.testing.assert_array_equal(S.cpu().numpy(), want)
+    # gradient with custom weights: dF_v = mask/nsel * (w_g * dS / sum_w) - against the oracle's backward
+    x = [dev(a).requires_grad_(True) for a in views_np]
+    S = model.group_fusion(model.view_pooling(x, dev(scheme), pool=pool, empty_fill=fill), dev(w))
+    dS = rng.standard_normal((B, D)).astype(np.float32)
+    S.backward(dev(dS))
+    want_dF = O.pool_fuse_bwd(dS, F, brow, G, pool, weights=w)
+    for v in range(V):
+        np.testing.assert_array_equal(x[v].grad.cpu().numpy(), want_dF[:, v, :])
+
+
+def test_reference_call_sequence_takes_the_default_weight_path(model):
+    """scheme = group_scheme(scores); w = group_weight(scheme); group_fusion(view_pooling(views, scheme), w):
+    the tensors carry provenance tags, so the scheme is not re-validated and the weights are known to be
+    1 + n_g; an in-place edit of either voids the tag and the general path gives the edited result."""
+    B, V, D, G = 33, 12, 2048, 10
+    rng = np.random.default_rng(9)
+    F = rng.standard_normal((B, V, D)).astype(np.float32)
+    scores = rng.uniform(0.02, 0.88, V).astype(np.float32)
+    views = [dev(F[:, v, :]) for v in range(V)]
+    scheme = model.group_scheme([[float(t) for t in scores]], G, V)
+    w = model.group_weight(scheme)
+    assert model._tag_of(scheme) is not None and model._tag_of(w) is not None
+    ref_scheme = O.group_scheme([scores], G, V)
+    np.testing.assert_array_equal(scheme.cpu().numpy(), ref_scheme)
+    want = O.group_fusion(O.view_pooling([F[:, v, :] for v in range(V)], ref_scheme), O.group_weight(ref_scheme))
+    got = model.group_fusion(model.view_pooling(views, scheme), w)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    w[0] += 2.0                                              # edited weights: the tag no longer applies
+    assert model._tag_of(w) is None
+    w_np = O.group_weight(ref_scheme)
+    w_np[0] += 2.0
+    want2 = O.group_fusion(O.view_pooling([F[:, v, :] for v in range(V)], ref_scheme), w_np)
+    np.testing.assert_array_equal(model.group_fusion(model.view_pooling(views, scheme), w).cpu().numpy(), want2)
+    # host (NumPy) scheme and weights, as the reference feeds them through placeholders (train.py:277-288)
+    got3 = model.group_fusion(model.view_pooling(views, ref_scheme), O.group_weight(ref_scheme))
+    np.testing.assert_array_equal(got3.cpu().numpy(), want)
+
+
+def test_group_fusion_accepts_a_plain_dict(model):
+    """nets/model.py:94-97 iterates any {index: tensor} dict: a hand-built dict, an edited GroupDescriptors and a
+    partial dict (denominator = the sum of ALL weights, :99) all work, with gradients to the entries."""
+    B, G, shape = 5, 6, (3, 3, 64)
+    rng = np.random.default_rng(21)
+    P = {g: rng.standard_normal((B,) + shape).astype(np.float32) for g in range(G)}
+    w = rng.uniform(0.5, 4.0, G).astype(np.float32)
+    want = O.group_fusion(P, w)
+    Pd = {g: dev(a).requires_grad_(True) for g, a in P.items()}
+    got = model.group_fusion(Pd, dev(w))
+    assert tuple(got.shape) == (B,) + shape
+    np.testing.assert_array_equal(got.detach().cpu().numpy(), want)
+    got.sum().backward()
+    sumw = np.float32(0)
+    for t in w:
+        sumw = np.float32(sumw + t)
+    for g in range(G):
+        np.testing.assert_array_equal(Pd[g].grad.cpu().numpy(), np.full((B,) + shape, np.float32(1) / sumw * w[g]))
+    # partial dict: missing groups contribute nothing to the numerator, everything to the denominator
+    part = {g: P[g] for g in (1, 4)}
+    want_p = (w[1] * P[1] + w[4] * P[4]) / sumw
+    np.testing.assert_array_equal(model.group_fusion({g: dev(a) for g, a in part.items()}, w).cpu().numpy(), want_p)
+    # an edited GroupDescriptors is a plain dict from then on
+    V, D = 6, 1024
+    F = rng.standard_normal((B, V, D)).astype(np.float32)
+    brow = np.array([0, 2, 2, 5, 5, 5], dtype=np.int32)
+    scheme = np.zeros((G, V), dtype=np.int32)
+    scheme[brow, np.arange(V)] = 1
+    desc = model.view_pooling([dev(F[:, v, :]) for v in range(V)], dev(scheme))
+    repl = rng.standard_normal((B, D)).astype(np.float32)
+    desc[3] = dev(repl)
+    ref_desc = O.view_pooling([F[:, v, :] for v in range(V)], scheme)
+    ref_desc[3] = repl
+    wg = O.group_weight(scheme)
+    np.testing.assert_array_equal(model.group_fusion(desc, dev(wg)).cpu().numpy(), O.group_fusion(ref_desc, wg))
+    with pytest.raises(IndexError):
+        model.group_fusion({7: dev(repl)}, dev(wg))
+
+
+@pytest.mark.parametrize("G", [4, 8, 10, 16])
+def test_group_scheme_literal_multiplier(model, G):
+    """nets/model.py:23 hard-codes `score * 10` whatever num_group is: multiplier=10 reproduces that (IndexError when
+    the bin does not fit num_group), the default multiplies by num_group; identical at 10."""
+    V = 12
+    rng = np.random.default_rng(G)
+    scores = rng.uniform(0.0, min(1.0, G / 10.0) * 0.999, V).astype(np.float32)
+    got = model.group_scheme([[float(t) for t in scores]], G, V, multiplier=10)
+    np.testing.assert_array_equal(got.cpu().numpy(), O.group_scheme([scores], G, V, multiplier=10))
+    np.testing.assert_array_equal(model.group_scheme([[float(t) for t in scores]], G, V).cpu().numpy(),
+                                  O.group_scheme([scores], G, V))
+    if G < 10:
+        bad = scores.copy()
+        bad[3] = np.float32((G + 0.5) / 10.0)                  # int(score * 10) == G: out of bounds in the reference
+        with pytest.raises(IndexError):
+            O.group_scheme([bad], G, V, multiplier=10)
+        with pytest.raises(IndexError):
+            model.group_scheme([[float(t) for t in bad]], G, V, multiplier=10)
 
 
 # ---------------------------------------------------------------- pooling + fusion
@@ -136,16 +262,11 @@ def test_pool_fuse_fwd_bwd_bit_exact_f32(model, pool, fill, B, V, D, G):
 def test_pool_variants_agree(model, variant, pool, B, V, D, G):
     """One-tile-per-CTA bulk-copy staging, plain-load staging and the persistent TMA ring are the
     same function (forward, tie mask and therefore backward)."""
-    from gvcnn_tf_b200 import _cabi
     F, bins, dS = make_inputs(77 + B, B, V, D, G, ties=True)
     x = dev(F).requires_grad_(True)
-    try:
-        assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
-        S = model.pool_fuse(x, dev(bins), G, pool=pool)
-        S.backward(dev(dS))                     # variants 1/2: generic backward; 3: V-templated backward
-        torch.cuda.synchronize()
-    finally:
-        _cabi.lib().gvcnn_set_pool_variant(0)
+    S = model.pool_fuse(x, dev(bins), G, pool=pool, _variant=variant)
+    S.backward(dev(dS))                     # variants 1/2: generic backward; 3: V-templated backward
+    torch.cuda.synchronize()
     np.testing.assert_array_equal(S.detach().cpu().numpy(), O.pool_fuse_fwd(F, bins, G, pool, 1.0))
     np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
 
@@ -364,9 +485,17 @@ def test_full_path_config2_properties(model, c_oracle):
     assert torch.equal(Sm2, 2 * Sm1)
 
 
-def test_host_buffer_entry_point(model):
+def _host_pipeline(L, streams=1):
+    import ctypes
+    pipe = ctypes.c_void_p()
+    assert L.gvcnn_host_pipeline_create(ctypes.byref(pipe), streams) == 0
+    return pipe
+
+
+@pytest.mark.parametrize("streams", [1, 2])
+def test_host_buffer_entry_point(model, streams):
     """gvcnn_grouping_fusion_host: pinned host buffers in, host buffers out, same bits as the
-    device-pointer path."""
+    device-pointer path; the pipeline object (streams + events) is reused across calls."""
     import ctypes
     from gvcnn_tf_b200 import _cabi as Cb
     B, V, D, G, Cr = 600, 12, 512, 8, 256
@@ -381,17 +510,103 @@ def test_host_buffer_entry_point(model):
     Wd, bd = dev(W), dev(b)
     L = Cb.lib()
     chunk = 256
-    nbytes = L.gvcnn_host_workspace_bytes(chunk, V, Cr, D, Cb.F32, 1)
+    nbytes = L.gvcnn_host_workspace_bytes(B, chunk, V, Cr, D, Cb.F32, 1, Cb.SCORE_REDUCE_SHAPE)
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = L.gvcnn_grouping_fusion_host(p(Rh), p(Fh), p(Wd), p(bd), p(Sh), p(sc), p(bn), p(dSh), p(dFh), p(st),
-                                      B, V, Cr, D, G, Cb.POOL_MAX, ctypes.c_float(1.0), Cb.F32, chunk, p(ws), nbytes)
-    assert rc == 0, L.gvcnn_strerror(rc)
-    sr = model.score_bin(dev(R), Wd, bd, G)
-    np.testing.assert_array_equal(bn.numpy(), sr.bins.cpu().numpy())
+    pipe = _host_pipeline(L, streams)
+    try:
+        for _ in range(2):                           # second call: same pipeline object, same answer
+            Sh.zero_(), dFh.zero_(), bn.zero_()
+            rc = L.gvcnn_grouping_fusion_host(pipe, p(Rh), p(Fh), p(Wd), p(bd), p(Sh), p(sc), p(bn), p(dSh), p(dFh), p(st),
+                                              B, V, Cr, D, G, Cb.POOL_MAX, ctypes.c_float(1.0), Cb.F32,
+                                              Cb.SCORE_REDUCE_SHAPE, B, None, None, chunk, p(ws), nbytes)
+            assert rc == 0, L.gvcnn_strerror(rc)
+            sr = model.score_bin(dev(R), Wd, bd, G)
+            np.testing.assert_array_equal(bn.numpy(), sr.bins.cpu().numpy())
+            np.testing.assert_array_equal(Sh.numpy(), O.pool_fuse_fwd(F, bn.numpy(), G))
+            np.testing.assert_array_equal(dFh.numpy(), O.pool_fuse_bwd(dS, F, bn.numpy(), G))
+    finally:
+        assert L.gvcnn_host_pipeline_destroy(pipe) == 0
+
+
+@pytest.mark.parametrize("training", [0, 1])
+def test_host_buffer_entry_point_literal_batch_mode(model, training):
+    """The reference's only mode (one scheme per batch, nets/model.py:146) through the host-buffer entry point:
+    two passes (R -> batch mean -> one bin row; F -> S), same bits as the device-pointer literal path and the
+    oracle; the exchange callback (SURVEY 8e collective (2)) is called exactly once, in stream order."""
+    import ctypes
+    from gvcnn_tf_b200 import _cabi as Cb
+    B, V, D, G, Cr = 700, 12, 1024, 8, 256
+    F, _, dS = make_inputs(41, B, V, D, G, ties=True)
+    R, W, b = score_inputs(42, B, V, Cr, bias_range=4.0)
+    Fh, Rh, dSh = (torch.tensor(a).pin_memory() for a in (F, R, dS))
+    Sh = torch.empty((B, D)).pin_memory()
+    dFh = torch.empty((B, V, D)).pin_memory()
+    sc = torch.empty((V,)).pin_memory()
+    bn = torch.empty((V,), dtype=torch.int32).pin_memory()
+    st = torch.zeros(4, dtype=torch.int32)
+    Wd, bd = dev(W), dev(b)
+    L = Cb.lib()
+    chunk = 128
+    nbytes = L.gvcnn_host_workspace_bytes(B, chunk, V, Cr, D, Cb.F32, training, Cb.SCORE_REDUCE_BATCH)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    calls = []
+
+    def _exchange(_user, xsum_ptr, n, stream):      # a 1-rank "all-reduce": identity, but it must be called
+        calls.append((n, bool(xsum_ptr)))
+        return 0
+    cb = Cb.EXCHANGE_FN(_exchange)
+    pipe = _host_pipeline(L)
+    try:
+        rc = L.gvcnn_grouping_fusion_host(pipe, p(Rh), p(Fh), p(Wd), p(bd), p(Sh), p(sc), p(bn),
+                                          p(dSh) if training else None, p(dFh) if training else None, p(st),
+                                          B, V, Cr, D, G, Cb.POOL_MAX, ctypes.c_float(1.0), Cb.F32,
+                                          Cb.SCORE_REDUCE_BATCH, B, cb, None, chunk, p(ws), nbytes)
+        assert rc == 0, L.gvcnn_strerror(rc)
+    finally:
+        L.gvcnn_host_pipeline_destroy(pipe)
+    assert calls == [(V, True)]
+    sr = model.score_bin(dev(R), Wd, bd, G, score_reduce="batch", clamp=True)
+    np.testing.assert_array_equal(bn.numpy(), sr.bins.cpu().numpy()[0])
+    np.testing.assert_array_equal(sc.numpy(), sr.scores.cpu().numpy()[0])
+    assert len(set(bn.tolist())) > 2                                    # the biases spread the batch means over bins
+    # the bins agree with the float64 value of the mathematics (except on flagged edges), S / dF with the oracle
+    x64, s64 = O.view_scores(R, W, b, score_reduce="batch", dtype=np.float64)
+    want_bins = O.bins_from_scores(s64.astype(np.float32), G)[0]
+    edge = O.edge_ulps_distance(s64.astype(np.float32), G, k=4)[0]
+    assert np.all((bn.numpy() == want_bins) | edge)
     np.testing.assert_array_equal(Sh.numpy(), O.pool_fuse_fwd(F, bn.numpy(), G))
-    np.testing.assert_array_equal(dFh.numpy(), O.pool_fuse_bwd(dS, F, bn.numpy(), G))
+    if training:
+        np.testing.assert_array_equal(dFh.numpy(), O.pool_fuse_bwd(dS, F, bn.numpy(), G))
+
+
+def test_literal_batch_forward_one_call(model):
+    """gvcnn_grouping_fusion_batch_fwd (the reference-literal forward, PDL-chained launches, no host hop) gives
+    the staged model API's bits; multiplier=10 is the literal `score * 10` of nets/model.py:23."""
+    import ctypes
+    from gvcnn_tf_b200 import _cabi as Cb
+    B, V, D, G, Cr = 300, 12, 2048, 10, 1024
+    F, _, _ = make_inputs(51, B, V, D, G, ties=True)
+    R, W, b = score_inputs(52, B, V, Cr, bias_range=4.0)
+    L = Cb.lib()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    Fd, Rd, Wd, bd = dev(F), dev(R), dev(W), dev(b)
+    x = torch.empty((B, V), device="cuda")
+    xsum, xm, sc = (torch.empty((V,), device="cuda") for _ in range(3))
+    bn = torch.empty((V,), dtype=torch.int32, device="cuda")
+    S = torch.empty((B, D), device="cuda")
+    st = torch.zeros(4, dtype=torch.int32, device="cuda")
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.gvcnn_grouping_fusion_batch_fwd(p(Rd), p(Wd), p(bd), p(Fd), p(x), p(xsum), p(xm), p(sc), p(bn), None, p(S),
+                                           None, p(st), B, V, Cr, D, G, 10, Cb.POOL_MAX, ctypes.c_float(1.0),
+                                           Cb.LAYOUT_BVD, Cb.LAYOUT_BVD, Cb.F32, 1, 0, B, None, None, sp)
+    assert rc == 0, L.gvcnn_strerror(rc)
+    S2, sr = model.grouping_fusion(Rd, Wd, bd, Fd, G, score_reduce="batch", multiplier=10, check=True)
+    assert torch.equal(S, S2) and torch.equal(bn, sr.bins[0]) and torch.equal(sc, sr.scores[0])
+    assert torch.equal(xm, sr.x[0])
+    np.testing.assert_array_equal(S.cpu().numpy(), O.pool_fuse_fwd(F, bn.cpu().numpy(), G))
 
 
 def test_head_module_trains(model):
@@ -837,13 +1052,9 @@ def test_one_call_forward_equals_staged_path(model, c_oracle, B, V, D, pool, dty
     outs = []
     for variant in (0, 1):                       # 0: ring / V-templated kernels; 1: generic one-tile-per-CTA kernels
         x = dev(F, td).requires_grad_(True)
-        try:
-            assert _cabi.lib().gvcnn_set_pool_variant(variant) == 0
-            S, sr = model.grouping_fusion(dev(R, td), dev(W), dev(b), x, G, pool=pool)
-            S.backward(dev(dS, td))
-            torch.cuda.synchronize()
-        finally:
-            _cabi.lib().gvcnn_set_pool_variant(0)
+        S, sr = model.grouping_fusion(dev(R, td), dev(W), dev(b), x, G, pool=pool, _variant=variant)
+        S.backward(dev(dS, td))
+        torch.cuda.synchronize()
         outs.append((S.detach().float().cpu().numpy(), sr.x.cpu().numpy(), sr.scores.cpu().numpy(),
                      sr.bins.cpu().numpy(), sr.flags.cpu().numpy(), x.grad.float().cpu().numpy()))
     for a, c in zip(outs[0], outs[1]):

@@ -26,6 +26,20 @@ def test_shard_range_partitions_exactly():
         parallel.shard_range(4, 2, 2)
 
 
+def test_every_rank_runs_the_same_number_of_steps():
+    """train_size=66, world=4, batch 4 gives shards of 17/17/16/16 shapes = 5/5/4/4 batches: a rank-local loop would
+    issue a different number of all-reduces per rank and hang NCCL.  steps_per_epoch is the largest rank's count, and
+    global_batch_size says how many shapes the literal batch mean of each step is over."""
+    for n, k, bs in ((66, 4, 4), (64, 8, 4), (7, 2, 4), (4096, 8, 512), (3, 4, 2)):
+        steps = parallel.steps_per_epoch(n, k, bs)
+        per_rank = [-(-(parallel.shard_range(n, r, k)[1] - parallel.shard_range(n, r, k)[0]) // bs) for r in range(k)]
+        assert steps == max(per_rank)
+        assert sum(parallel.global_batch_size(n, k, bs, st) for st in range(steps)) == n
+        assert all(parallel.global_batch_size(n, k, bs, st) > 0 for st in range(steps))
+        assert parallel.global_batch_size(n, k, bs, steps) == 0
+    assert parallel.steps_per_epoch(66, 4, 4) == 5
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
