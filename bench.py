@@ -348,7 +348,7 @@ def run_cuda_arm(args):
                 "grouping_fusion_fwd")
 
     def k_fwd_batch(i, with_mask=False):
-        # reference-literal forward entry point: x, column sums, [exchange], one bin row, pool+fuse (4-5 launches, PDL)
+        # reference-literal forward entry point: x; column sums + [exchange] + one bin row; pool+fuse (3 launches, PDL)
         o = outs[i % NSETS]
         Fd, Rd, _ = sets[i % NSETS]
         C.check(L.gvcnn_grouping_fusion_batch_fwd(p(Rd), p(Wd), p(bias_lit), p(Fd), p(o["x"]), p(o["xsum"]), None,
@@ -357,27 +357,35 @@ def run_cuda_arm(args):
                                                   pool, fill, C.LAYOUT_BVD, C.LAYOUT_BVD, C.F32, 0, 1, global_count,
                                                   ex_fn, ex_user, sp), "grouping_fusion_batch_fwd")
 
+    ar_stream = torch.cuda.Stream(priority=-1) if world > 1 else None   # the bucket's own (high-priority) stream
+
     def grad_allreduce():
+        """sum over ranks * 1/K of the gradient bucket, forked off the step's stream so it overlaps the dF kernel."""
         if world == 1:
             return None
-        if comm is not None:                                         # one kernel: sum over ranks * 1/K, in stream order
-            comm.all_reduce_(grad_bucket, 1.0 / world)
-            return None
+        if comm is not None:                                         # the library's one-kernel NVLink all-reduce
+            ar_stream.wait_stream(torch.cuda.current_stream())
+            comm.all_reduce_(grad_bucket, 1.0 / world, stream=ar_stream)
+            return "join"
         return dist.all_reduce(grad_bucket, op=dist.ReduceOp.AVG, async_op=True)
+
+    def grad_join(work):
+        if work == "join":
+            torch.cuda.current_stream().wait_stream(ar_stream)
+        elif work is not None:
+            work.wait()
 
     def step_train_batch(i):
         k_fwd_batch(i, True)
         work = grad_allreduce()                                      # launched before, and overlapping, the dF kernel
         k_bwd(i, shared=True)
-        if work is not None:
-            work.wait()
+        grad_join(work)
 
     def step_train_shape(i):
         k_fwd_shape(i, True)
         work = grad_allreduce()
         k_bwd(i, shared=False)
-        if work is not None:
-            work.wait()
+        grad_join(work)
 
     def barrier():
         if world > 1:
@@ -513,7 +521,8 @@ def run_cuda_arm(args):
     if sampler:
         sampler.start()
     ms_fwd = timed(k_fwd_batch, K, graph_fwd)
-    fwd_launches = 4 + (1 if (world > 1 and comm is not None) else 0)
+    # view_score, fused (column sums + exchange + mean/score/bin), pool+fuse; the NCCL route is 5 launches + NCCL's
+    fwd_launches = 3 if (world == 1 or comm is not None) else 4
 
     # ---- the per-shape mode (SURVEY.md 8d's heavier general case; round 1's headline): 2 launches, no exchange
     graph_shape = make_graph(k_fwd_shape)
@@ -534,9 +543,7 @@ def run_cuda_arm(args):
     us_allreduce, us_allreduce_nccl, us_xsum = None, None, None
     if world > 1:
         def step_allreduce(i):
-            w = grad_allreduce()
-            if w is not None:
-                w.wait()
+            grad_join(grad_allreduce())
         for i in range(3):
             step_allreduce(i)
         us_allreduce = timed(step_allreduce, K) / K * 1e3

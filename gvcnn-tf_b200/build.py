@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libgvcnn_sm100.so")
-SOURCES = ["capi.cu", "host_pipeline.cu", "comm.cu", "score.cu", "scheme.cu", "pool_fwd.cu", "pool_fwd_ring.cu", "pool_gap_ring.cu", "pool_bwd.cu", "pool_bwd_fast.cu", "paper_mode.cu"]
+SOURCES = ["capi.cu", "host_pipeline.cu", "comm.cu", "score.cu", "gap_score.cu", "scheme.cu", "pool_fwd.cu", "pool_fwd_ring.cu", "pool_gap_ring.cu", "pool_bwd.cu", "pool_bwd_fast.cu", "paper_mode.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ring_common.cuh"), os.path.join(ROOT, "include", "gvcnn_b200.h")]
 
 
@@ -34,8 +34,9 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: A/B builds of the same sources with -D flags into another path (scripts/_build/)."""
+    if out is None and not force and not needs_build():
         return SO
     cmd = [
         nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
@@ -43,8 +44,8 @@ def build(force=False, verbose=False):
         "-fmad=false",                      # one rounding per float32 op unless fmaf() is written
         "-Xcompiler", "-fPIC", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", SO,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+        "-o", out or SO,
+    ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
@@ -57,8 +58,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libgvcnn_sm100.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -3,7 +3,7 @@
 // chunked host-buffer pipeline is in host_pipeline.cu.  Nothing here touches torch.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "comm_dev.cuh"
 
 using namespace gvcnn;
 
@@ -64,6 +64,39 @@ int check_dims(int B, int V, int64_t D, int G, int dtype)
 bool is_aligned(const void *p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
 
 }  // namespace
+
+namespace gvcnn {
+// Tail of the literal score stage: x [B, V] -> xsum [V] -> [exchange] -> mean, score, bin (one [V] row).
+// Fast form: ONE kernel does the column sums, the cross-rank exchange (when the exchange is the library's own
+// communicator) and the mean / score / bin.  Any other exchange callback (e.g. NCCL through torch.distributed), or
+// more views than the fused kernel covers, takes the staged form: three launches.
+int batch_score_tail(const float *x, float *xsum, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                     int32_t *status, int B, int V, int G, int multiplier, int edge_ulps, int clamp,
+                     int64_t global_count, gvcnn_exchange_fn exchange, void *exchange_user, cudaStream_t st)
+{
+    const CommPeers *peers = nullptr;
+    int crank = 0, cworld = 1;
+    const bool own_comm = exchange == &gvcnn_comm_allreduce_f32 && comm_device_view(exchange_user, &peers, &crank, &cworld);
+    int rc = -1000;
+    if (!exchange || own_comm)
+        rc = launch_batch_mean_bin_fused(x, xsum, x_mean, scores, bins, flags, status, B, V, G, multiplier, edge_ulps,
+                                         clamp, (float)global_count, own_comm ? peers : nullptr, crank, cworld, st);
+    if (rc != -1000) return rc;
+    if (B == 0 || !x) {
+        const cudaError_t e = cudaMemsetAsync(xsum, 0, (size_t)V * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        rc = gvcnn_batch_sum_x(x, xsum, B, V, st);
+        if (rc) return rc;
+    }
+    if (exchange) {  // SURVEY.md 8e collective (2): every rank bins the same global-batch mean
+        rc = exchange(exchange_user, xsum, V, st);
+        if (rc) return rc;
+    }
+    return gvcnn_score_bin(xsum, (float)global_count, x_mean, scores, bins, flags, status, V, G, multiplier, edge_ulps,
+                           clamp, st);
+}
+}  // namespace gvcnn
 
 extern "C" {
 
@@ -183,6 +216,29 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias, float 
                              edge_ulps, clamp, static_cast<cudaStream_t>(stream));
 }
 
+// GlobalAveragePooling2D + Dense(1) (+ score, bin) from the raw maps, nets/model.py:144-147: one pass, no [B, V, C] hop
+int gvcnn_gap_score_bin_fwd(const void *maps, const float *W, const float *bias, float *R_out, float *x, float *scores,
+                            int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int HW, int C, int G,
+                            int m_layout, int dtype, int fuse_bin, int edge_ulps, int clamp, void *stream)
+{
+    if (HW <= 0 || C <= 0) return GVCNN_E_BAD_ARG;
+    const int64_t D = (int64_t)HW * C;
+    int rc = check_dims(B, V, D, G, dtype);
+    if (rc) return rc == kEmptyBatch ? 0 : rc;
+    if (!W || !bias || edge_ulps < 0) return GVCNN_E_BAD_ARG;
+    if (fuse_bin ? (!scores || !bins) : !x) return GVCNN_E_BAD_ARG;
+    if (!is_aligned(W, 16) || !is_aligned(bias, 4) || (R_out && !is_aligned(R_out, 16))) return GVCNN_E_MISALIGNED;
+    ViewPtrs mp;
+    int64_t sb;
+    bool al;
+    rc = make_view_ptrs(maps, m_layout, dtype, B, V, D, mp, sb, al);
+    if (rc) return rc;
+    if (!al) return GVCNN_E_UNSUPPORTED;
+    rc = launch_gap_score(mp, sb, W, bias, R_out, x, scores, bins, flags, status, B, V, HW, C, G, dtype, fuse_bin != 0,
+                          edge_ulps, clamp, static_cast<cudaStream_t>(stream));
+    return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
+}
+
 int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b, const float *weights,
                         int64_t weight_stride_b, void *S, void *group_desc, uint8_t *tie_mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float empty_fill,
                         int f_layout, int dtype, void *stream)
@@ -296,21 +352,12 @@ int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *
     if (global_count < B || global_count <= 0) return GVCNN_E_BAD_ARG;
     if ((pool & 0xff) != GVCNN_POOL_MAX && (pool & 0xff) != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (empty) {
-        const cudaError_t e = cudaMemsetAsync(xsum, 0, (size_t)V * sizeof(float), st);
-        if (e != cudaSuccess) return (int)e;
-    } else {
+    if (!empty) {
         rc = gvcnn_view_score_fwd(R, W, bias, x, B, V, C, r_layout, dtype, stream);
         if (rc) return rc;
-        rc = gvcnn_batch_sum_x(x, xsum, B, V, stream);
-        if (rc) return rc;
     }
-    if (exchange) {  // SURVEY.md 8e collective (2): every rank bins the same global-batch mean
-        rc = exchange(exchange_user, xsum, V, stream);
-        if (rc) return rc;
-    }
-    rc = gvcnn_score_bin(xsum, (float)global_count, x_mean, scores, bins, flags, status, V, G, multiplier, edge_ulps,
-                         clamp, stream);
+    rc = batch_score_tail(empty ? nullptr : x, xsum, x_mean, scores, bins, flags, status, B, V, G, multiplier, edge_ulps,
+                          clamp, global_count, exchange, exchange_user, st);
     if (rc || empty) return rc;
     return gvcnn_pool_fuse_fwd(F, bins, 0, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
                                f_layout, dtype, stream);

@@ -2,75 +2,45 @@
 //   (1) the flat parameter-gradient bucket of the training step, V * (C_raw + 1) floats = 49 KB at V = 12 - the
 //       B200-native form of `nccl_ops.all_sum(grads)` + `* 1/K` at utils/_train_helper.py:17-31;
 //   (2) the V per-view partial sums of the literal batch mean before binning (nets/model.py:146 on a sharded batch).
-// Both are latency-bound (an NCCL all-reduce of this size costs 20-33 us on 2-8 B200s against a 100-180 us step), so
-// they get ONE kernel per rank and no rendezvous on the host:
-//   push   every rank stores its vector into its own slot of EVERY peer's receive buffer (plain stores to
-//          cudaIpc-mapped peer memory: NVLink writes), then a system-scope release store of the call's sequence
-//          number into its flag at every peer;
-//   wait   spin (acquire loads of LOCAL memory) until all ranks' flags show this sequence number;
-//   reduce add the slots in rank order 0..K-1 - the same order on every rank, so all ranks get bit-identical sums
+// Both are latency-bound (an NCCL all-reduce of this size costs 18-33 us on 2-8 B200s against a 100-190 us step), so
+// they get ONE kernel per rank, no rendezvous on the host, and a protocol with a single NVLink hop:
+//   push   every rank stores its vector into its own slot of EVERY peer's receive buffer (cudaIpc-mapped peer memory:
+//          NVLink stores) as low-latency elements {value, sequence number} - one 8-byte single-copy-atomic store per
+//          float (comm_dev.cuh), so no fence and no separate flag follow;
+//   wait   poll the LOCAL slots until every element carries this call's sequence number;
+//   reduce add the K slots in rank order 0..K-1 - the same order on every rank, so all ranks get bit-identical sums
 //          (every rank must derive the same bins) - scale, write in place.
-// Channels: the vector is cut into fixed 2048-float channels, one CTA each, with private slots, flags and sequence
-// counters, so CTAs never synchronise with each other.  Slots are double-buffered by sequence parity: a rank can
-// only push call s+2 after it has finished call s+1, i.e. after every peer has pushed s+1, i.e. after every peer has
-// finished READING call s - no second barrier.  The sequence counters live in device memory and are advanced by
-// the kernel, so a captured launch replays correctly from a CUDA graph.
+// (Round 2's first version pushed plain data, fenced with __threadfence_system() and then released a flag: 10.5 us per
+// 12-float exchange between 2 GPUs against 19.2 us for NCCL; the fence + flag cost a second NVLink round trip.)
+// Channels: the vector is cut into fixed 2048-float channels, one CTA each, with private slots and sequence counters,
+// so CTAs never synchronise with each other.  Slots are double-buffered by sequence parity: a rank can only push call
+// s+2 after it has finished call s+1, i.e. after every peer has pushed s+1, i.e. after every peer has finished READING
+// call s - no second barrier.  The sequence counters live in device memory and are advanced by the kernel, so a
+// captured launch replays correctly from a CUDA graph.  The fused batch-mean kernel of score.cu speaks the same
+// protocol on channel 0 (it IS an all-reduce of V floats, issued from inside the kernel that needs the result).
 // A rank that never arrives would hang its peers: the wait gives up after kCommTimeoutNs and raises an error word the
 // host can read (gvcnn_comm_error), instead of hanging the GPU.
 #include <cstring>
 #include <new>
 
-#include "common.cuh"
+#include "comm_dev.cuh"
 
 using namespace gvcnn;
 
 namespace {
-constexpr int kCommMaxWorld = GVCNN_COMM_MAX_WORLD;
-constexpr int kChanFloats = 2048;                                    // one CTA's share
-constexpr int kCommMaxChan = GVCNN_COMM_MAX_FLOATS / kChanFloats;    // 8
-constexpr int kCommThreads = 512;                                    // one float4 each per pass
-constexpr unsigned long long kCommTimeoutNs = 4000000000ull;         // 4 s
-
-// device view of one rank's receive buffer
-struct CommBuf {
-    float data[2][kCommMaxWorld][GVCNN_COMM_MAX_FLOATS];    // [phase][source rank][float]
-    uint32_t flag[2][kCommMaxWorld][kCommMaxChan][8];       // [phase][source rank][channel], padded to 32 B
-    uint32_t seq[kCommMaxChan][8];                          // local: last sequence number used per channel
-    uint32_t error;                                         // local: set when a wait timed out
-};
-
-struct CommPeers {
-    CommBuf *buf[kCommMaxWorld];
-};
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
+constexpr int kCommThreads = 512;  // one float4 (4 LL elements) each
 
 __global__ void __launch_bounds__(kCommThreads)
 allreduce_oneshot_kernel(const CommPeers peers, const int rank, const int world, float *__restrict__ data, const int n,
                          const float scale)
 {
     const int c = blockIdx.x;
-    const int lo = c * kChanFloats;
-    const int cnt = min(n - lo, kChanFloats);            // floats of this channel (> 0 by the grid size)
+    const int lo = c * kCommChanFloats;
+    const int cnt = min(n - lo, kCommChanFloats);        // floats of this channel (> 0 by the grid size)
     CommBuf *mine = peers.buf[rank];
     const uint32_t seq = mine->seq[c][0] + 1u;           // every thread reads it before thread 0 advances it below
     const int phase = (int)(seq & 1u);
-    const int i = threadIdx.x * 4;                       // this thread's float4 of the channel
+    const int i = threadIdx.x * 4;                       // this thread's 4 floats of the channel
     const bool vec_ok = (i + 3 < cnt) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
     float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (vec_ok) {
@@ -80,42 +50,32 @@ allreduce_oneshot_kernel(const CommPeers peers, const int rank, const int world,
         for (int j = 0; j < 4; ++j)
             if (i + j < cnt) v[j] = data[lo + i + j];
     }
-    // ---- push: my slot at every peer (own buffer included), farthest-first rotation to spread the links
+    __syncthreads();                                     // all reads of seq[c] are done
+    if (threadIdx.x == 0) mine->seq[c][0] = seq;
     if (i < cnt) {
+        // ---- push: my slot at every peer (own buffer included), rotated so the ranks do not all hit one link first
         for (int d = 0; d < world; ++d) {
             const int p = (rank + 1 + d) % world;
-            float *dst = &peers.buf[p]->data[phase][rank][lo + i];
-            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);  // slots are 16-byte aligned, padded
+            uint2 *dst = &peers.buf[p]->ll[phase][rank][lo + i];  // 32-byte aligned; slots are padded to 4 elements
+            ll_store2(dst, v[0], v[1], seq);
+            ll_store2(dst + 2, v[2], v[3], seq);
         }
-    }
-    __threadfence_system();
-    __syncthreads();                                     // all of this CTA's stores are ordered before the flags
-    if ((int)threadIdx.x < world) st_release_sys(&peers.buf[threadIdx.x]->flag[phase][rank][c][0], seq);
-    if (threadIdx.x == 0) mine->seq[c][0] = seq;
-    // ---- wait: every source rank's flag for this channel and phase
-    if ((int)threadIdx.x < world) {
-        const uint32_t *f = &mine->flag[phase][threadIdx.x][c][0];
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(f) != seq) {
-            if (global_timer_ns() - t0 > kCommTimeoutNs) {
-                atomicExch(&mine->error, 1u);
-                break;
+        // ---- wait + reduce in rank order (identical on every rank), scale, store in place
+        const unsigned long long t0 = comm_timer_ns();
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        bool ok = true;
+        for (int r = 0; r < world; ++r) {
+            const uint2 *src = &mine->ll[phase][r][lo + i];
+            float t[4];
+            ok = ok && ll_wait2(src, seq, t[0], t[1], t0) && ll_wait2(src + 2, seq, t[2], t[3], t0);
+            if (!ok) break;
+            if (r == 0) {
+                for (int j = 0; j < 4; ++j) acc[j] = t[j];
+            } else {
+                for (int j = 0; j < 4; ++j) acc[j] = __fadd_rn(acc[j], t[j]);
             }
         }
-    }
-    __syncthreads();
-    // ---- reduce in rank order (identical on every rank), scale, store in place
-    if (i < cnt) {
-        float acc[4];
-        {
-            const float4 t = __ldcg(reinterpret_cast<const float4 *>(&mine->data[phase][0][lo + i]));
-            acc[0] = t.x; acc[1] = t.y; acc[2] = t.z; acc[3] = t.w;
-        }
-        for (int r = 1; r < world; ++r) {
-            const float4 t = __ldcg(reinterpret_cast<const float4 *>(&mine->data[phase][r][lo + i]));
-            acc[0] = __fadd_rn(acc[0], t.x); acc[1] = __fadd_rn(acc[1], t.y);
-            acc[2] = __fadd_rn(acc[2], t.z); acc[3] = __fadd_rn(acc[3], t.w);
-        }
+        if (!ok) atomicExch(&mine->error, 1u);
         if (scale != 1.0f)
             for (int j = 0; j < 4; ++j) acc[j] = __fmul_rn(acc[j], scale);
         if (vec_ok) {
@@ -140,7 +100,7 @@ extern "C" {
 int gvcnn_comm_create(gvcnn_comm **out, int rank, int world, void *handle_out)
 {
     static_assert(GVCNN_COMM_HANDLE_BYTES >= sizeof(cudaIpcMemHandle_t), "handle size");
-    static_assert(kChanFloats == kCommThreads * 4, "one float4 per thread per channel");
+    static_assert(kCommChanFloats == kCommThreads * 4, "one float4 per thread per channel");
     if (!out || !handle_out || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world) return GVCNN_E_BAD_ARG;
     *out = nullptr;
     int rc = gvcnn_check_device();
@@ -197,7 +157,7 @@ int gvcnn_comm_allreduce_scaled_f32(void *comm, float *data_dev, int n, float sc
     if (!c || !data_dev || n <= 0 || n > GVCNN_COMM_MAX_FLOATS) return GVCNN_E_BAD_ARG;
     if (!c->connected && c->world > 1) return GVCNN_E_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(data_dev) % 4) return GVCNN_E_MISALIGNED;
-    const int nchan = (n + kChanFloats - 1) / kChanFloats;
+    const int nchan = (n + kCommChanFloats - 1) / kCommChanFloats;
     allreduce_oneshot_kernel<<<nchan, kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(c->peers, c->rank, c->world,
                                                                                            data_dev, n, scale);
     return (int)cudaGetLastError();
@@ -207,6 +167,23 @@ int gvcnn_comm_allreduce_f32(void *comm, float *data_dev, int n, void *stream)
 {
     return gvcnn_comm_allreduce_scaled_f32(comm, data_dev, n, 1.0f, stream);
 }
+
+}  // extern "C"
+
+namespace gvcnn {
+// for the fused kernels of other translation units: the device view of a connected communicator
+bool comm_device_view(void *comm, const CommPeers **peers, int *rank, int *world)
+{
+    gvcnn_comm *c = static_cast<gvcnn_comm *>(comm);
+    if (!c || (!c->connected && c->world > 1)) return false;
+    *peers = &c->peers;
+    *rank = c->rank;
+    *world = c->world;
+    return true;
+}
+}  // namespace gvcnn
+
+extern "C" {
 
 int gvcnn_comm_error(gvcnn_comm *c)
 {

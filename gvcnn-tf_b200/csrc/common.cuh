@@ -118,11 +118,25 @@ __device__ __forceinline__ uint4 ldg_stream_16(const void *p)
                  : "l"(p), "l"(pol));
     return r;
 }
+// write-once data (S, dF).  GVCNN_STORE_POLICY (compile time, for A/B builds): 0 = st.global.cs (streaming, the
+// default), 1 = L2 evict-first policy object, 2 = plain st.global (write-back, normal priority).
+#ifndef GVCNN_STORE_POLICY
+#define GVCNN_STORE_POLICY 0
+#endif
 __device__ __forceinline__ void stg_stream_16(void *p, const uint4 &v)
 {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w)
+#if GVCNN_STORE_POLICY == 1
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
                  : "memory");
+#elif GVCNN_STORE_POLICY == 2
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -230,6 +244,21 @@ inline cudaError_t ensure_dyn_smem(int bytes)
     e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev].store(bytes, std::memory_order_relaxed);
     return e;
+}
+
+// CTAs of `Kern` that fit on one SM (occupancy calculator), asked once per kernel instantiation.
+template <auto Kern>
+inline int resident_ctas(int threads, size_t dyn_smem = 0)
+{
+    static std::atomic<int> cached{0};
+    int n = cached.load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern, threads, dyn_smem) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = 1;
+    }
+    cached.store(n, std::memory_order_relaxed);
+    return n;
 }
 
 // A/B tuning knobs are environment variables read ONCE per process (first use), never per launch.
@@ -374,6 +403,9 @@ int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const fl
                       float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int C,
                       int G, int dtype, bool aligned16, bool fuse_bin, int edge_ulps, int clamp,
                       cudaStream_t st);
+int launch_gap_score(const ViewPtrs &mp, int64_t m_sb, const float *W, const float *bias, float *R_out, float *x,
+                     float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int HW, int C, int G,
+                     int dtype, bool fuse_bin, int edge_ulps, int clamp, cudaStream_t st);
 int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st);
 int launch_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
                      int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, bool x_is_score,

@@ -15,7 +15,7 @@
 //     bins), so the copy engine never idles: the call stays bound by the host->device link like the one-pass mode.
 #include <new>
 
-#include "common.cuh"
+#include "comm_dev.cuh"
 
 using namespace gvcnn;
 
@@ -200,13 +200,9 @@ int gvcnn_grouping_fusion_host(gvcnn_host_pipeline *pipe, const void *R_host, co
                                        dtype, s_k);
             GVCNN_CK(cudaEventRecord(pipe->ev_r[i], s_k));
         }
-        if (err == cudaSuccess && krc == 0) {
-            if (B > 0) krc = gvcnn_batch_sum_x(d_x, d_xsum, B, V, s_k);
-            else GVCNN_CK(cudaMemsetAsync(d_xsum, 0, (size_t)V * 4, s_k));
-        }
-        if (err == cudaSuccess && krc == 0 && exchange) krc = exchange(exchange_user, d_xsum, V, s_k);
         if (err == cudaSuccess && krc == 0)
-            krc = gvcnn_score_bin(d_xsum, (float)global_count, nullptr, d_scores1, d_bins1, nullptr, d_status, V, G, 0, 0, 1, s_k);
+            krc = batch_score_tail(B > 0 ? d_x : nullptr, d_xsum, nullptr, d_scores1, d_bins1, nullptr, d_status, B, V, G,
+                                   0, 0, 1, global_count, exchange, exchange_user, s_k);
     }
 
     // ---- main pass: (R,) F (, dS) in; kernels; S (, scores, bins, dF) out

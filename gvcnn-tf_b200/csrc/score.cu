@@ -9,7 +9,7 @@
 // restated in oracle/gvcnn_oracle.c (oracle_view_score_x_kernel_order):
 //   lane l accumulates chunks (i*32 + l) of E consecutive elements with one
 //   fmaf chain, lanes combine with offsets 16,8,4,2,1, bias is added last.
-#include "common.cuh"
+#include "comm_dev.cuh"
 
 namespace gvcnn {
 
@@ -90,14 +90,19 @@ view_score_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict
 // 16,8,4,2,1 (a + b is commutative, so which lane holds which row's partial sum does not matter),
 // bias last - oracle_view_score_x_kernel_order with LPR = 32.  C is a compile-time multiple of the
 // 32-lane x 16-byte x NB batch: no bounds checks.
-constexpr int kFastRows = 4;  // rows (shapes) per warp
+constexpr int kFastRows = 4;  // rows (shapes) per transposing butterfly
 
+// A warp owns `rpw` consecutive shapes of one view (a multiple of 4) and streams them as one continuous software
+// pipeline, four rows per butterfly.  The launcher picks rpw so that the whole grid is ONE resident wave (see
+// launch_view_score_t): with 4 rows per warp the grid was 2.59 waves of 592 resident CTAs and the last, 59 % full
+// wave left the memory system under-used for a third of the kernel (ncu: DRAM 69.6 %, profiles/r01z_ncu_full.md).
 template <typename T, int NB, bool FUSE_BIN>  // NB = 16-byte loads per lane per row = C / (32 * E)
 __global__ void __launch_bounds__(kScoreWarps * 32)
 view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict__ W,
                        const float *__restrict__ bias, float *__restrict__ x_out, float *__restrict__ scores,
                        int32_t *__restrict__ bins, int32_t *__restrict__ flag_out, int32_t *status, const int B,
-                       const int V, const int G, const int edge_ulps, const int clamp, const int64_t items)
+                       const int V, const int G, const int edge_ulps, const int clamp, const int64_t items,
+                       const int rpw)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int C = NB * 32 * E;
@@ -107,62 +112,69 @@ view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__res
     pdl_launch_dependents();
     if (item >= items) return;
     const int v = (int)(item % V);
-    const int b0 = (int)(item / V) * kFastRows;
+    const int b_first = (int)(item / V) * rpw;
+    const int b_end = min(b_first + rpw, B);
     const T *__restrict__ r0 = reinterpret_cast<const T *>(rp.p[v]) + lane * E;
     const float *__restrict__ w = W + (int64_t)v * C + lane * E;
+    const float bv = __ldg(bias + v);
 
     uint4 buf[2][NB];
-    float acc[kFastRows];
 #pragma unroll
-    for (int u = 0; u < NB; ++u) buf[0][u] = ldg_stream_16(r0 + (int64_t)min(b0, B - 1) * r_sb + u * 32 * E);
+    for (int u = 0; u < NB; ++u) buf[0][u] = ldg_stream_16(r0 + (int64_t)min(b_first, B - 1) * r_sb + u * 32 * E);
+    for (int b0 = b_first; b0 < b_end; b0 += kFastRows) {
+        float acc[kFastRows];
 #pragma unroll
-    for (int j = 0; j < kFastRows; ++j) {
-        if (j + 1 < kFastRows) {
-            const T *rn = r0 + (int64_t)min(b0 + j + 1, B - 1) * r_sb;
+        for (int j = 0; j < kFastRows; ++j) {
+            // next row (of this group, or the first of the next group) in flight while this one is multiplied;
+            // rows past the batch end are clamped duplicates whose results are dropped
+            const int bn = b0 + j + 1;
+            if (j + 1 < kFastRows || bn < b_end) {
+                const T *rn = r0 + (int64_t)min(bn, B - 1) * r_sb;
 #pragma unroll
-            for (int u = 0; u < NB; ++u) buf[(j + 1) & 1][u] = ldg_stream_16(rn + u * 32 * E);
-        }
-        float a = 0.0f;
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            float f[E];
-            Elem<T>::unpack(buf[j & 1][u], f);
-#pragma unroll
-            for (int q = 0; q < E; q += 4) {
-                const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + u * 32 * E + q));
-                a = fmaf(f[q + 0], wv.x, a);
-                a = fmaf(f[q + 1], wv.y, a);
-                a = fmaf(f[q + 2], wv.z, a);
-                a = fmaf(f[q + 3], wv.w, a);
+                for (int u = 0; u < NB; ++u) buf[(j + 1) & 1][u] = ldg_stream_16(rn + u * 32 * E);
             }
-        }
-        acc[j] = a;
-    }
-    // transposing butterfly: after offsets 16 and 8, lane group (lane >> 3) holds row (lane >> 3)
-    const bool hi = (lane & 16) != 0;
-    float k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
-    const float s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
-    k0 = __fadd_rn(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
-    k1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
-    const bool h8 = (lane & 8) != 0;
-    float k = h8 ? k1 : k0;
-    const float sd = h8 ? k0 : k1;
-    k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, sd, 8));
+            float a = 0.0f;
 #pragma unroll
-    for (int off = 4; off >= 1; off >>= 1) k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, k, off));
+            for (int u = 0; u < NB; ++u) {
+                float f[E];
+                Elem<T>::unpack(buf[j & 1][u], f);
+#pragma unroll
+                for (int q = 0; q < E; q += 4) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + u * 32 * E + q));
+                    a = fmaf(f[q + 0], wv.x, a);
+                    a = fmaf(f[q + 1], wv.y, a);
+                    a = fmaf(f[q + 2], wv.z, a);
+                    a = fmaf(f[q + 3], wv.w, a);
+                }
+            }
+            acc[j] = a;
+        }
+        // transposing butterfly: after offsets 16 and 8, lane group (lane >> 3) holds row (lane >> 3)
+        const bool hi = (lane & 16) != 0;
+        float k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
+        const float s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
+        k0 = __fadd_rn(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
+        k1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
+        const bool h8 = (lane & 8) != 0;
+        float k = h8 ? k1 : k0;
+        const float sd = h8 ? k0 : k1;
+        k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, sd, 8));
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, k, off));
 
-    const int b = b0 + (lane >> 3);
-    if ((lane & 7) == 0 && b < B) {
-        const int64_t row = (int64_t)b * V + v;
-        const float x = __fadd_rn(k, __ldg(bias + v));
-        if (x_out) x_out[row] = x;
-        if constexpr (FUSE_BIN) {
-            float s;
-            int bin;
-            const int flags = score_and_bin(x, 1.0f, G, edge_ulps, clamp, s, bin);
-            scores[row] = s;
-            bins[row] = bin;
-            publish(flags, flag_out ? flag_out + row : nullptr, status);
+        const int b = b0 + (lane >> 3);
+        if ((lane & 7) == 0 && b < b_end) {
+            const int64_t row = (int64_t)b * V + v;
+            const float x = __fadd_rn(k, bv);
+            if (x_out) x_out[row] = x;
+            if constexpr (FUSE_BIN) {
+                float s;
+                int bin;
+                const int flags = score_and_bin(x, 1.0f, G, edge_ulps, clamp, s, bin);
+                scores[row] = s;
+                bins[row] = bin;
+                publish(flags, flag_out ? flag_out + row : nullptr, status);
+            }
         }
     }
 }
@@ -210,6 +222,97 @@ __global__ void __launch_bounds__(256) score_bin_kernel(const float *__restrict_
     publish(flags, flag_out ? flag_out + i : nullptr, status);
 }
 
+// The literal batch mode's tail in ONE launch (nets/model.py:146-147, :23 on a batch that may be sharded over GPUs).
+// One CTA per view - nothing in this stage couples the views, so the CTAs never talk to each other:
+//   xsum[v] = sum_b x[b, v]          batch_sum_x_kernel's code and order (thread t adds b = t, t + 256, ...; warp
+//                                    butterflies; the 8 warp sums in warp order)
+//   [COMM]  all-reduce of that ONE float over the ranks: low-latency push of {value, sequence} to every peer's
+//           receive buffer over NVLink, poll the local slots, add in rank order (comm_dev.cuh; the communicator's
+//           per-view lane `llv`, with a per-view sequence counter, so view v's exchange is independent of the others)
+//   xm = xsum / denom, s = |xm| / (1 + |xm|), bin = (int)(s * (mult or G))     score_bin_kernel's epilogue
+// Replaces three launches (batch_sum_x, the exchange kernel, score_bin) and two full-grid completions; the collective
+// is issued from inside the kernel that needs its result.
+template <bool COMM>
+__global__ void __launch_bounds__(256)
+batch_mean_bin_fused_kernel(const float *__restrict__ x, float *__restrict__ xsum, float *__restrict__ x_mean,
+                            float *__restrict__ scores, int32_t *__restrict__ bins, int32_t *__restrict__ flag_out,
+                            int32_t *status, const int B, const int V, const int G, const int mult, const int edge_ulps,
+                            const int clamp, const float denom, const CommPeers peers, const int rank, const int world)
+{
+    __shared__ float warp_sum[8];
+    __shared__ float parts[kCommMaxWorld];
+    const int v = blockIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    float acc = 0.0f;
+    for (int b = threadIdx.x; b < B; b += 256) acc = __fadd_rn(acc, x[(int64_t)b * V + v]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float sum = 0.0f;
+    if (threadIdx.x < 32) {  // warp 0: every lane computes the same total (thread 0's is the one batch_sum_x stores)
+        sum = warp_sum[0];
+        for (int i = 1; i < 8; ++i) sum = __fadd_rn(sum, warp_sum[i]);
+        if constexpr (COMM) {
+            CommBuf *mine = peers.buf[rank];
+            const int lane = threadIdx.x;
+            const uint32_t seq = mine->seqv[v] + 1u;
+            const int phase = (int)(seq & 1u);
+            __syncwarp();
+            if (lane == 0) mine->seqv[v] = seq;
+            if (lane < world) ll_store1(&peers.buf[(rank + 1 + lane) % world]->llv[phase][rank][v], sum, seq);
+            float val = 0.0f;
+            if (lane < world && !ll_wait1(&mine->llv[phase][lane][v], seq, val, comm_timer_ns())) atomicExch(&mine->error, 1u);
+            sum = __shfl_sync(0xffffffffu, val, 0);  // rank order: bit-identical on every rank
+            for (int r = 1; r < world; ++r) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, val, r));
+        }
+    }
+    if (threadIdx.x == 0) {
+        xsum[v] = sum;
+        float s;
+        int bin;
+        const int flags = score_and_bin(sum, denom, G, edge_ulps, clamp, s, bin, false, mult);
+        if (x_mean) x_mean[v] = __fdiv_rn(sum, denom);
+        if (scores) scores[v] = s;
+        bins[v] = bin;
+        publish(flags, flag_out ? flag_out + v : nullptr, status);
+    }
+}
+
+int launch_batch_mean_bin_fused(const float *x, float *xsum, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                                int32_t *status, int B, int V, int G, int multiplier, int edge_ulps, int clamp,
+                                float denom, const CommPeers *peers, int rank, int world, cudaStream_t st)
+{
+    if (V > GVCNN_MAX_VIEWS) return -1000;
+    cudaError_t err;
+    if (peers && world > 1) {
+        err = launch_pdl(batch_mean_bin_fused_kernel<true>, dim3(V), dim3(256), 0, st, x, xsum, x_mean, scores, bins,
+                         flags, status, B, V, G, multiplier, edge_ulps, clamp, denom, *peers, rank, world);
+    } else {
+        CommPeers none = {};
+        err = launch_pdl(batch_mean_bin_fused_kernel<false>, dim3(V), dim3(256), 0, st, x, xsum, x_mean, scores, bins,
+                         flags, status, B, V, G, multiplier, edge_ulps, clamp, denom, none, 0, 1);
+    }
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaGetLastError();
+}
+
+static int score_sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            return 148;
+        }
+        cached = n;
+    }
+    return cached;
+}
+
 template <typename T>
 static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,
                                float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V,
@@ -220,11 +323,21 @@ static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W,
     cudaError_t err = cudaSuccess;
     if (vec && (C == 8 * 32 * Elem<T>::kVec || C == 4 * 32 * Elem<T>::kVec)) {
         // C_raw = 1024 (block3 of ResNet-v2-50, nets/resnet_v2.py:242) is the reference's only width
-        const int64_t items = (int64_t)V * ((B + kFastRows - 1) / kFastRows);
-        const dim3 fgrid((unsigned)((items + kScoreWarps - 1) / kScoreWarps)), fblock(kScoreWarps * 32);
+        // rows per warp: the smallest multiple of 4 for which all CTAs are resident at once (one wave; the CTAs per SM
+        // come from the occupancy calculator for the instantiation).  B = 4096, V = 12, fp32 on 148 SMs: 3 CTAs of 8
+        // warps per SM -> 16 rows per warp, 384 CTAs on 444 slots.
+        static const int env_rpw = env_int_once("GVCNN_SCORE_RPW", 0);  // A/B knob: 4 = one butterfly per warp (round 1)
+        const dim3 fblock(kScoreWarps * 32);
 #define GVCNN_LAUNCH_FAST(NB_, FUSE_)                                                                        \
-    err = launch_pdl(view_score_fast_kernel<T, NB_, FUSE_>, fgrid, fblock, 0, st, rp, r_sb, W, bias, x, scores, \
-                     bins, flags, status, B, V, G, edge_ulps, clamp, items)
+    do {                                                                                                     \
+        const int64_t warp_slots = (int64_t)score_sm_count() * resident_ctas<view_score_fast_kernel<T, NB_, FUSE_>>(kScoreWarps * 32) * kScoreWarps; \
+        int rpw = (int)(kFastRows * ((rows + kFastRows * warp_slots - 1) / (kFastRows * warp_slots)));       \
+        if (env_rpw >= kFastRows && env_rpw % kFastRows == 0) rpw = env_rpw;                                 \
+        const int64_t items = (int64_t)V * ((B + rpw - 1) / rpw);                                            \
+        const dim3 fgrid((unsigned)((items + kScoreWarps - 1) / kScoreWarps));                               \
+        err = launch_pdl(view_score_fast_kernel<T, NB_, FUSE_>, fgrid, fblock, 0, st, rp, r_sb, W, bias, x,  \
+                         scores, bins, flags, status, B, V, G, edge_ulps, clamp, items, rpw);                \
+    } while (0)
         if (C == 8 * 32 * Elem<T>::kVec) {
             if (fuse_bin) GVCNN_LAUNCH_FAST(8, true); else GVCNN_LAUNCH_FAST(8, false);
         } else {

@@ -201,6 +201,21 @@ def _new_status(dev):
     return torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
 
 
+def _raw_views(R, layout, c_raw):
+    """The raw view descriptors in either form the reference has them in: already pooled ([N, C_raw] per view,
+    after GlobalAveragePooling2D, nets/model.py:144) or the block3 maps themselves ([N, h, w, C_raw] per view,
+    channel-last) - told apart by the trailing shape against the Dense(1) kernel's C_raw.  Returns (_Views, HW)."""
+    rv = _Views(R, layout, "R")
+    HW = 1
+    if c_raw > 0 and rv.D != c_raw:
+        last = rv.view_shape[-1]
+        if last != c_raw or rv.D % c_raw:
+            raise ValueError("raw view descriptors: trailing dimension %d does not match the score kernel's C_raw = %d"
+                             % (last, c_raw))
+        HW = rv.D // c_raw
+    return rv, HW
+
+
 def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulps=1, clamp=False,
               check=True, process_group=None, multiplier=None, status=None, exchange=None,
               global_count=None) -> ScoreResult:
@@ -208,6 +223,9 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
 
     R: raw view descriptors after GAP (nets/model.py:144), [B, V, C] ('bvd'),
        [V, B, C] ('vbd') or a list of V [B, C] tensors; float32 or bfloat16.
+       Or the raw MAPS before the GAP ([B, V, h, w, C] / [V, B, h, w, C] / list of V [N, h, w, C], channel-last -
+       end_points['resnet_v2_50/block3']): the GlobalAveragePooling2D of nets/model.py:144 then runs inside the
+       score kernel (gvcnn_gap_score_bin_fwd) and the pooled [B, V, C] tensor is never written.
     W [V, C], b [V]: the V separate Dense(1) layers (nets/model.py:145), float32.
     score_reduce 'shape': one score per (shape, view), bins [B, V] - the
        reference at batch size 1 per shape.  'batch': the literal
@@ -220,14 +238,15 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
        with raise_for_status instead of synchronising every step); with check=False and no status given
        nothing is recorded.
     """
-    rv = _Views(R, layout, "R")
     _require_cuda(W, "W"), _require_cuda(b, "b")
     if W.dtype != torch.float32 or b.dtype != torch.float32:
         raise TypeError("W and b must be float32")
     Wc, bc = W.contiguous(), b.contiguous()
-    if tuple(Wc.shape) != (rv.V, rv.D) or tuple(bc.shape) != (rv.V,):
+    rv, HW = _raw_views(R, layout, int(Wc.shape[-1]) if Wc.dim() == 2 else -1)
+    Craw = rv.D // HW
+    if tuple(Wc.shape) != (rv.V, Craw) or tuple(bc.shape) != (rv.V,):
         raise ValueError("W must be [V, C] = %s and b [V], got %s and %s"
-                         % ((rv.V, rv.D), tuple(Wc.shape), tuple(bc.shape)))
+                         % ((rv.V, Craw), tuple(Wc.shape), tuple(bc.shape)))
     dev = rv.device
     L = C.lib()
     if status is None and check:
@@ -239,14 +258,24 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
                 raise ValueError("multiplier is only selectable with score_reduce='batch' or through group_scheme")
             buf = torch.empty((4, rv.B, rv.V), dtype=torch.int32, device=dev)      # x, scores, bins, flags: one allocation
             x, scores, bins, flags = buf[0].view(torch.float32), buf[1].view(torch.float32), buf[2], buf[3]
-            C.check(L.gvcnn_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(x), _ptr(scores), _ptr(bins),
-                                          _ptr(flags), _ptr(status), rv.B, rv.V, rv.D, num_group,
-                                          rv.layout, dt, edge_ulps, int(clamp), _stream()),
-                    "gvcnn_score_bin_fwd")
+            if HW > 1:      # raw maps: GlobalAveragePooling2D folded into the score kernel (nets/model.py:144-145)
+                C.check(L.gvcnn_gap_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), None, _ptr(x), _ptr(scores), _ptr(bins),
+                                                  _ptr(flags), _ptr(status), rv.B, rv.V, HW, Craw, num_group, rv.layout,
+                                                  dt, 1, edge_ulps, int(clamp), _stream()), "gvcnn_gap_score_bin_fwd")
+            else:
+                C.check(L.gvcnn_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(x), _ptr(scores), _ptr(bins),
+                                              _ptr(flags), _ptr(status), rv.B, rv.V, rv.D, num_group,
+                                              rv.layout, dt, edge_ulps, int(clamp), _stream()),
+                        "gvcnn_score_bin_fwd")
         elif score_reduce == "batch":
             xb = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
-            C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb), rv.B, rv.V, rv.D,
-                                           rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
+            if HW > 1:
+                C.check(L.gvcnn_gap_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), None, _ptr(xb), None, None, None, None,
+                                                  rv.B, rv.V, HW, Craw, 1, rv.layout, dt, 0, 0, 0, _stream()),
+                        "gvcnn_gap_score_bin_fwd")
+            else:
+                C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb), rv.B, rv.V, rv.D,
+                                               rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
             buf = torch.empty((5, 1, rv.V), dtype=torch.int32, device=dev)
             xsum, x, scores = (buf[i].view(torch.float32) for i in range(3))
             bins, flags = buf[3], buf[4]
@@ -792,6 +821,28 @@ def _fused_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, want_mask, s
     return S, x, scores, bins, flags, mask
 
 
+def _is_raw_maps(raw, W, layout):
+    """True when `raw` holds the un-pooled block3 maps ([..., h, w, C_raw]) rather than [..., C_raw] descriptors."""
+    if not (isinstance(W, torch.Tensor) and W.dim() == 2):
+        return False
+    t = raw[0] if isinstance(raw, (list, tuple)) and len(raw) else raw
+    if not isinstance(t, torch.Tensor):
+        return False
+    lead = 1 if isinstance(raw, (list, tuple)) else 2
+    return t.dim() > lead + 1 and t.shape[-1] == W.shape[1]
+
+
+_EXCHANGE_PROTO = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
+
+
+def _callable_exchange(exchange):
+    """(function pointer, user) as the C entry points take it -> (callable, user) as score_bin calls it."""
+    fn, user = exchange
+    if isinstance(fn, ctypes.c_void_p):
+        fn = _EXCHANGE_PROTO(fn.value)
+    return fn, user
+
+
 class _FusedFwdFn(torch.autograd.Function):
     """Per-shape scores + bins + pooling + fusion through gvcnn_grouping_fusion_fwd (two launches chained
     with programmatic dependent launch, no host hop); backward = the pooling/fusion backward (dF only, as
@@ -839,6 +890,16 @@ def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_grou
     if status is None and check:
         dev0 = W.device if isinstance(W, torch.Tensor) else None
         status = _new_status(dev0)
+    if _is_raw_maps(raw_view_descriptors, W, layout):
+        # block3 maps instead of pooled raw descriptors: the GAP of nets/model.py:144 runs inside the score kernel
+        # (gvcnn_gap_score_bin_fwd); pooling + fusion follow on the stream, chained with programmatic dependent launch
+        sr = score_bin(raw_view_descriptors, W, b, num_group, score_reduce=score_reduce, layout=layout,
+                       edge_ulps=edge_ulps, clamp=clamp, check=check, process_group=process_group, status=status,
+                       multiplier=multiplier, exchange=(None if exchange is None else _callable_exchange(exchange)),
+                       global_count=global_count)
+        S = pool_fuse(final_view_descriptors, sr.bins, num_group, pool=pool, empty_fill=empty_fill, layout=layout,
+                      _variant=_variant)
+        return S, sr
     if score_reduce == "shape":
         if multiplier not in (None, num_group):
             raise ValueError("multiplier is only selectable with score_reduce='batch' or through group_scheme")

@@ -143,6 +143,25 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias,
                         int32_t *status, int B, int V, int C, int G,
                         int r_layout, int dtype, int edge_ulps, int clamp, void *stream);
 
+/* GlobalAveragePooling2D + Dense(1) (+ score + bin) straight from the raw view maps,
+ * nets/model.py:144-147: maps = per-view channel-last feature
+ * maps [B, V, HW, C] / [V, B, HW, C] / V pointers to [B, HW, C] (m_layout; the
+ * reference: end_points['resnet_v2_50/block3'], [N, 10, 10, 1024] per view).
+ *   R[b, v, c] = (sum over the HW positions, fixed order) / HW   (tf.reduce_mean)
+ *   x[b, v]    = sum_c R[b, v, c] * W[v, c] + bias[v]             (float32 maps: == gvcnn_view_score_fwd on R, bit
+ *                for bit; bf16 maps: the same fixed order with the bf16 kernels' lane-to-channel mapping)
+ * fuse_bin != 0: also scores / bins / flags [B, V] like gvcnn_score_bin_fwd (per-shape
+ * mode; x may be null); fuse_bin == 0: only x (feed gvcnn_batch_sum_x / gvcnn_score_bin
+ * for the literal batch mode; scores / bins may be null).  R_out (nullable): the
+ * pooled raw descriptor, float32 [B, V, C].  The [B, V, C] tensor is otherwise never
+ * written.  Supported: 16-byte aligned rows and C = 512 / 1024 (f32), 1024 / 2048
+ * (bf16); anything else returns GVCNN_E_UNSUPPORTED (pool first, then
+ * gvcnn_score_bin_fwd). */
+int gvcnn_gap_score_bin_fwd(const void *maps, const float *W, const float *bias, float *R_out,
+                            float *x, float *scores, int32_t *bins, int32_t *flags, int32_t *status,
+                            int B, int V, int HW, int C, int G, int m_layout, int dtype,
+                            int fuse_bin, int edge_ulps, int clamp, void *stream);
+
 /* --- scheme / weight glue (the reference's host NumPy part) -----------------
  * gvcnn_bins_from_scores: model.group_scheme's arithmetic on already-computed
  *   scores (nets/model.py:23): bin = (int)(float32(s) * float32(multiplier or G));

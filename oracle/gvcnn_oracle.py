@@ -39,7 +39,7 @@ __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion",
     "view_scores", "score_from_x", "bins_from_scores", "edge_ulps_distance",
     "pool_fuse_fwd", "pool_fuse_bwd", "grouping_fusion_fwd", "round_bf16",
-    "sorted_view_order", "tie_mask_planes",
+    "sorted_view_order", "tie_mask_planes", "gap_mean_kernel_order", "add_n",
 ]
 
 
@@ -132,19 +132,52 @@ def view_pooling(final_view_descriptors, group_scheme, pool="max", empty_fill=1.
     return group_descriptors
 
 
-def group_fusion(group_descriptors, group_weight):
+def add_n(terms, association="left"):
+    """tf.add_n(terms) (nets/model.py:100), one float32 rounding per addition, in one of two association orders:
+
+    'left'  ((t0 + t1) + t2) + ...   - the op-order MODEL the CUDA kernels implement and are held bit-exact to;
+    'tf8'   TensorFlow's CPU AddN kernel as remembered from tensorflow/core/kernels/aggregate_ops.cc (NOT verifiable
+            here - no TensorFlow in this image): the first r = N % 8 inputs (r = 8 when N % 8 == 0, r = 9 when
+            N % 8 == 1) are added left to right into the output, then every further block of 8 inputs is summed
+            left to right and added to the output as ONE term:  out = out + (((t_r + t_r+1) + ...) + t_r+7).
+            N = 10 (the reference's only num_group): (t0 + t1) + (t2 + ... + t9).  Identical to 'left' for N <= 9.
+    The two differ in the last bits only; tests hold the CUDA result within the north star's 1e-5 of BOTH."""
+    terms = list(terms)
+    n = len(terms)
+    if association == "left" or n <= 9:
+        acc = terms[0]
+        for t in terms[1:]:
+            acc = acc + t
+        return acc
+    if association != "tf8":
+        raise ValueError(association)
+    r = n % 8
+    if r == 0:
+        r = 8
+    elif r == 1:
+        r = 9
+    acc = terms[0]
+    for t in terms[1:r]:
+        acc = acc + t
+    while r < n:
+        blk = terms[r]
+        for t in terms[r + 1:r + 8]:
+            blk = blk + t
+        acc = acc + blk
+        r += 8
+    return acc
+
+
+def group_fusion(group_descriptors, group_weight, association="left"):
     """S = add_n_g(w_g * P_g) / sum_g w_g.  Follows nets/model.py:77-102:
     multiply per group (:97), reduce_sum of the weights (:99), add_n in dict
-    order 0..G-1 accumulated left to right, one true division (:100)."""
+    order 0..G-1 (``association``: see add_n), one true division (:100)."""
     w = np.asarray(group_weight, dtype=np.float32)
     numerator = [w[key] * value for key, value in group_descriptors.items()]
     denominator = np.float32(0)
     for x in w:
         denominator = np.float32(denominator + x)
-    acc = numerator[0]
-    for t in numerator[1:]:
-        acc = acc + t
-    return acc / denominator
+    return add_n(numerator, association) / denominator
 
 
 # --------------------------------------------------------------------------
@@ -180,6 +213,30 @@ def view_scores(R, W, b, score_reduce="shape", dtype=np.float64):
     elif score_reduce != "shape":
         raise ValueError(score_reduce)
     return x, score_from_x(x)
+
+
+def gap_mean_kernel_order(maps, nslices=8):
+    """GlobalAveragePooling2D of channel-last maps (nets/model.py:144: [N, h, w, C] -> [N, C]) = tf.reduce_mean over
+    the positions: a float32 sum, then ONE division by the count.  TF's own summation order (Eigen's tree) is not
+    reproducible without TF, so the order restated here is the CUDA kernel's (csrc/gap_score.cu): the HW positions are
+    cut into `nslices` contiguous slices (the first HW % nslices have one more), each summed sequentially from 0.0, the
+    slice sums added in ascending order, then divided by HW.  maps [..., HW, C] float32 -> [..., C] float32."""
+    m = np.asarray(maps, dtype=np.float32)
+    HW = m.shape[-2]
+    q, r = divmod(HW, nslices)
+    parts = []
+    p0 = 0
+    for s_ in range(nslices):
+        n = q + (1 if s_ < r else 0)
+        acc = np.zeros(m.shape[:-2] + m.shape[-1:], dtype=np.float32)
+        for p in range(p0, p0 + n):
+            acc = acc + m[..., p, :]
+        parts.append(acc)
+        p0 += n
+    tot = parts[0]
+    for a in parts[1:]:
+        tot = tot + a
+    return (tot / np.float32(HW)).astype(np.float32)
 
 
 def score_from_x(x):
@@ -238,7 +295,7 @@ def round_bf16(x):
     return np.where(np.isnan(x), x, out)
 
 
-def pool_fuse_fwd(F, bins, num_group, pool="max", empty_fill=1.0):
+def pool_fuse_fwd(F, bins, num_group, pool="max", empty_fill=1.0, association="left"):
     """Pooling + fusion for a whole batch with per-shape bin maps.
 
     F [B, V, D] float32, bins [B, V] (or [V], shared by the batch).  Runs the
@@ -262,7 +319,7 @@ def pool_fuse_fwd(F, bins, num_group, pool="max", empty_fill=1.0):
         w = group_weight(scheme)
         views = [F[sel, v, :] for v in range(V)]
         desc = view_pooling(views, scheme, pool=pool, empty_fill=empty_fill)
-        S[sel] = group_fusion(desc, w)
+        S[sel] = group_fusion(desc, w, association)
     return S
 
 

@@ -239,6 +239,112 @@ def test_group_scheme_literal_multiplier(model, G):
             model.group_scheme([[float(t) for t in bad]], G, V, multiplier=10)
 
 
+@pytest.mark.parametrize("G", [10, 16])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
+def test_fused_descriptor_within_tolerance_of_both_add_n_orders(model, G, pool, fill):
+    """What can differ from live TensorFlow: the association order of tf.add_n over the G weighted
+    group descriptors.  The kernels are bit-exact to the left-to-right model; against TensorFlow's CPU AddN blocking
+    (2 + 8 for the reference's num_group = 10, as remembered - unverifiable here) they are held to the north star's
+    tolerance: |diff| <= 1e-5 * |S| + 1e-5 * max|w_g P_g| / sum_w (the second term covers cancelling sums)."""
+    B, V, D = 64, 12, 2048
+    F, bins, _ = make_inputs(700 + G, B, V, D, G, ties=False)
+    S = model.pool_fuse(dev(F), dev(bins), G, pool=pool, empty_fill=fill).cpu().numpy()
+    left = O.pool_fuse_fwd(F, bins, G, pool, fill, association="left")
+    tf8 = O.pool_fuse_fwd(F, bins, G, pool, fill, association="tf8")
+    np.testing.assert_array_equal(S, left)
+    scale = (1 + V) * np.abs(F).max() / (G + V)
+    assert np.all(np.abs(S - tf8) <= RTOL_F32 * np.abs(tf8) + RTOL_F32 * scale)
+    assert np.any(S != tf8)                     # the orders really differ at these group counts
+
+
+# ---------------------------------------------------------------- GAP in front of the score FC (nets/model.py:144)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("B,V,h,w,Cr,G", [(4, 6, 10, 10, 1024, 10), (8, 6, 8, 8, 1024, 10), (3, 12, 10, 10, 512, 8),
+                                           (5, 12, 1, 3, 1024, 8), (2, 20, 7, 7, 1024, 16)])
+def test_gap_folded_into_the_score_kernel(model, c_oracle, dtype, B, V, h, w, Cr, G):
+    """GlobalAveragePooling2D(block3) -> Dense(1) -> score -> bin in one pass over the raw maps
+    (gvcnn_gap_score_bin_fwd): the pooled descriptor R equals the oracle's restatement of the kernel's summation
+    order bit for bit, x / scores / bins equal the score kernel's on that R bit for bit, and R is within float32
+    rounding of the float64 mean (TF's own summation order is not reproducible)."""
+    import ctypes
+    from gvcnn_tf_b200 import _cabi as Cb
+    rng = np.random.default_rng(B * 1000 + V * 10 + h)
+    maps = rng.standard_normal((B, V, h, w, Cr)).astype(np.float32)
+    Wn = rng.uniform(-0.08, 0.08, (V, Cr)).astype(np.float32)
+    bn = rng.uniform(-0.5, 0.5, V).astype(np.float32)
+    td = torch.float32
+    if dtype == "bf16":
+        if Cr == 512:
+            pytest.skip("bf16 rows of 512 channels are 1 KB: not an instantiated width")
+        maps, td = O.round_bf16(maps), torch.bfloat16
+    HW = h * w
+    R_want = O.gap_mean_kernel_order(maps.reshape(B, V, HW, Cr))
+    R64 = maps.reshape(B, V, HW, Cr).astype(np.float64).mean(axis=2)
+    np.testing.assert_allclose(R_want, R64, rtol=0, atol=2e-6)
+    # through the C ABI, with the pooled descriptor requested
+    L = Cb.lib()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    md, Wd, bd = dev(maps, td), dev(Wn), dev(bn)
+    R_out = torch.empty((B, V, Cr), device="cuda")
+    x = torch.empty((B, V), device="cuda")
+    sc = torch.empty((B, V), device="cuda")
+    bi = torch.empty((B, V), dtype=torch.int32, device="cuda")
+    fl = torch.empty((B, V), dtype=torch.int32, device="cuda")
+    st = torch.zeros(4, dtype=torch.int32, device="cuda")
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.gvcnn_gap_score_bin_fwd(p(md), p(Wd), p(bd), p(R_out), p(x), p(sc), p(bi), p(fl), p(st), B, V, HW, Cr, G,
+                                   Cb.LAYOUT_BVD, Cb.BF16 if dtype == "bf16" else Cb.F32, 1, 1, 0, sp)
+    assert rc == 0, L.gvcnn_strerror(rc)
+    np.testing.assert_array_equal(R_out.cpu().numpy(), R_want)
+    # the score part is the score kernel's arithmetic on that (float32) R, bit for bit: lane l owns the chunks
+    # (u * 32 + l) of E elements, E = 16 bytes of the MAPS' dtype (4 for float32 maps, 8 for bfloat16 maps)
+    E = 8 if dtype == "bf16" else 4
+    xk = c_oracle.view_score_x_kernel_order(R_want, Wn, bn, E=E)
+    np.testing.assert_array_equal(x.cpu().numpy(), xk)
+    sk = c_oracle.score_f32(xk)
+    np.testing.assert_array_equal(sc.cpu().numpy(), sk)
+    np.testing.assert_array_equal(bi.cpu().numpy(), O.bins_from_scores(sk, G))
+    if dtype == "f32":      # ... which for float32 maps is exactly gvcnn_score_bin_fwd on the pooled descriptor
+        sr = model.score_bin(dev(R_want), Wd, bd, G, edge_ulps=1)
+        assert torch.equal(x, sr.x) and torch.equal(sc, sr.scores) and torch.equal(bi, sr.bins) and torch.equal(fl, sr.flags)
+    # the Python mirror takes the maps wherever it takes pooled descriptors: list of V [N, h, w, C] (the reference's
+    # end_points['resnet_v2_50/block3'] per view), per-shape and per-batch scores
+    views = [md[:, v].contiguous() for v in range(V)]
+    sr2 = model.score_bin(views, Wd, bd, G, edge_ulps=1)
+    assert torch.equal(sr2.bins, bi) and torch.equal(sr2.x, x)
+    srb = model.score_bin(md, Wd, bd, G, score_reduce="batch", clamp=True)
+    if dtype == "f32":
+        srb_ref = model.score_bin(dev(R_want), Wd, bd, G, score_reduce="batch", clamp=True)
+        assert torch.equal(srb.bins, srb_ref.bins) and torch.equal(srb.scores, srb_ref.scores)
+    else:                   # float64 value of the batch mean, bins equal except on flagged edges
+        xm64 = (R64 * Wn[None].astype(np.float64)).sum(axis=2).mean(axis=0) + bn
+        s64 = (np.abs(xm64) / (1 + np.abs(xm64))).astype(np.float32)
+        assert np.all((srb.bins.cpu().numpy()[0] == O.bins_from_scores(s64, G)) | O.edge_ulps_distance(s64, G, k=64))
+
+
+def test_head_accepts_block3_maps(model):
+    """GVCNNHead / grouping_fusion with the raw block3 maps: same outputs as with the pooled descriptors computed
+    by the same kernel order, and no eager mean on the path."""
+    torch.manual_seed(3)
+    N, V, Cr, Cf, G = 4, 6, 1024, 2048, 10
+    head = model.GVCNNHead(V, Cr, Cf, 5, num_group=G, score_reduce="shape").cuda()
+    raw_maps = torch.randn(N, V, 10, 10, Cr, device="cuda")
+    final = [torch.randn(N, 10, 10, Cf, device="cuda", requires_grad=True) for _ in range(V)]
+    scores, S, logits = head(raw_maps, final)
+    R = torch.tensor(O.gap_mean_kernel_order(raw_maps.reshape(N, V, 100, Cr).cpu().numpy()), device="cuda")
+    scores2, S2, logits2 = head(R, final)
+    assert torch.equal(scores, scores2) and torch.equal(S, S2) and torch.equal(logits, logits2)
+    logits.sum().backward()
+    assert all(f.grad is not None for f in final)
+    # literal batch mode and the GAP-folded tail as well
+    head_b = model.GVCNNHead(V, Cr, Cf, 5, num_group=G, score_reduce="batch").cuda()
+    with torch.no_grad():
+        head_b.score_bias.uniform_(-3, 3)
+    sa, Sa, la = head_b(raw_maps, final, fold_gap=True)
+    sb, Sb, lb = head_b(R, final, fold_gap=True)
+    assert torch.equal(sa, sb) and torch.equal(Sa, Sb)
+
+
 # ---------------------------------------------------------------- pooling + fusion
 @pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0), ("max", 0.0), ("mean", 1.0)])
 @pytest.mark.parametrize("B,V,D,G", [

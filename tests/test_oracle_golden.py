@@ -266,3 +266,27 @@ def test_power_of_two_mean_shortcut_is_exact_in_float32():
             assert r * n == 1.0                                     # the reciprocal is exact
             a, b = (x * r).view(np.uint32), (x / n).view(np.uint32)
             assert np.array_equal(a, b), k
+
+
+def test_add_n_association_orders():
+    """The oracle's add_n in both association orders: identical up to 9 terms, (t0 + t1) + (t2 + ... + t9) for the
+    reference's num_group = 10, two blocks of 8 for 16; the two orders agree to float32 rounding."""
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 8, 9):
+        t = [rng.standard_normal(50).astype(np.float32) for _ in range(n)]
+        np.testing.assert_array_equal(O.add_n(t, "left"), O.add_n(t, "tf8"))
+    t = [rng.standard_normal(4000).astype(np.float32) for _ in range(10)]
+    blk = t[2]
+    for a in t[3:]:
+        blk = blk + a
+    np.testing.assert_array_equal(O.add_n(t, "tf8"), (t[0] + t[1]) + blk)
+    assert np.any(O.add_n(t, "tf8") != O.add_n(t, "left"))
+    np.testing.assert_allclose(O.add_n(t, "tf8"), O.add_n(t, "left"), rtol=0, atol=4e-6)
+    t = [rng.standard_normal(100).astype(np.float32) for _ in range(16)]
+    a = t[0]
+    for x in t[1:8]:
+        a = a + x
+    b = t[8]
+    for x in t[9:]:
+        b = b + x
+    np.testing.assert_array_equal(O.add_n(t, "tf8"), a + b)
