@@ -25,7 +25,7 @@ def pool_variant(pool, variant=0):
     return pool | (variant << 8)
 STATUS_WORDS = 4
 STATUS_BIN_RANGE, STATUS_NAN, STATUS_NEAR_EDGE, STATUS_BAD_SCHEME = 0, 1, 2, 3
-FLAG_NEAR_EDGE, FLAG_BIN_RANGE, FLAG_NAN = 1, 2, 4
+FLAG_NEAR_EDGE, FLAG_BIN_RANGE, FLAG_NAN, FLAG_ORDER_EDGE = 1, 2, 4, 8
 MAX_VIEWS, MAX_GROUPS = 128, 4096
 E_UNSUPPORTED = -10
 E_COMM_TIMEOUT = -11
@@ -38,9 +38,9 @@ SIGNATURES = {
     "gvcnn_version": (_i, []),
     "gvcnn_strerror": (ctypes.c_char_p, [_i]),
     "gvcnn_check_device": (_i, []),
-    "gvcnn_view_score_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "gvcnn_view_score_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_batch_sum_x": (_i, [_vp, _vp, _i, _i, _vp]),
-    "gvcnn_score_bin": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "gvcnn_score_bin": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
     "gvcnn_score_bin_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_gap_score_bin_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gvcnn_bins_from_scores": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),

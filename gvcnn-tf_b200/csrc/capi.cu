@@ -94,7 +94,7 @@ int batch_score_tail(const float *x, float *xsum, float *x_mean, float *scores, 
         if (rc) return rc;
     }
     return gvcnn_score_bin(xsum, (float)global_count, x_mean, scores, bins, flags, status, V, G, multiplier, edge_ulps,
-                           clamp, st);
+                           clamp, nullptr, 0, st);
 }
 }  // namespace gvcnn
 
@@ -138,19 +138,19 @@ int gvcnn_check_device(void)
     return major == 10 ? 0 : GVCNN_E_NO_DEVICE;
 }
 
-int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x, int B, int V, int C,
+int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x, float *xabs, int B, int V, int C,
                          int r_layout, int dtype, void *stream)
 {
     int rc = check_dims(B, V, C, 1, dtype);
     if (rc) return rc == kEmptyBatch ? 0 : rc;
     if (!W || !bias || !x) return GVCNN_E_BAD_ARG;
-    if (!is_aligned(W, 4) || !is_aligned(bias, 4) || !is_aligned(x, 4)) return GVCNN_E_MISALIGNED;
+    if (!is_aligned(W, 4) || !is_aligned(bias, 4) || !is_aligned(x, 4) || !is_aligned(xabs, 4)) return GVCNN_E_MISALIGNED;
     ViewPtrs rp;
     int64_t sb;
     bool al;
     rc = make_view_ptrs(R, r_layout, dtype, B, V, C, rp, sb, al);
     if (rc) return rc;
-    return launch_view_score(rp, sb, W, bias, x, nullptr, nullptr, nullptr, nullptr, B, V, C, 1, dtype, al,
+    return launch_view_score(rp, sb, W, bias, x, xabs, nullptr, nullptr, nullptr, nullptr, B, V, C, 1, dtype, al,
                              false, 0, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -161,13 +161,14 @@ int gvcnn_batch_sum_x(const float *x, float *xsum, int B, int V, void *stream)
 }
 
 int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
-                    int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, void *stream)
+                    int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, const float *xabs,
+                    int bound_terms, void *stream)
 {
     if (!x || !bins || n <= 0 || G <= 0 || multiplier < 0) return GVCNN_E_BAD_ARG;
     if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
-    if (edge_ulps < 0) return GVCNN_E_BAD_ARG;
+    if (edge_ulps < 0 || (xabs && bound_terms <= 0)) return GVCNN_E_BAD_ARG;
     return launch_score_bin(x, denom, x_mean, scores, bins, flags, status, n, G, multiplier, edge_ulps, clamp, false,
-                            static_cast<cudaStream_t>(stream));
+                            xabs, bound_terms, static_cast<cudaStream_t>(stream));
 }
 
 int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, int32_t *status, int64_t n,
@@ -176,7 +177,7 @@ int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, i
     if (!scores || !bins || n <= 0 || G <= 0 || multiplier < 0 || edge_ulps < 0) return GVCNN_E_BAD_ARG;
     if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
     return launch_score_bin(scores, 1.0f, nullptr, nullptr, bins, flags, status, n, G, multiplier, edge_ulps, clamp, true,
-                            static_cast<cudaStream_t>(stream));
+                            nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 int gvcnn_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, void *stream)
@@ -212,7 +213,7 @@ int gvcnn_score_bin_fwd(const void *R, const float *W, const float *bias, float 
     bool al;
     rc = make_view_ptrs(R, r_layout, dtype, B, V, C, rp, sb, al);
     if (rc) return rc;
-    return launch_view_score(rp, sb, W, bias, x, scores, bins, flags, status, B, V, C, G, dtype, al, true,
+    return launch_view_score(rp, sb, W, bias, x, nullptr, scores, bins, flags, status, B, V, C, G, dtype, al, true,
                              edge_ulps, clamp, static_cast<cudaStream_t>(stream));
 }
 
@@ -353,7 +354,7 @@ int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *
     if ((pool & 0xff) != GVCNN_POOL_MAX && (pool & 0xff) != GVCNN_POOL_MEAN) return GVCNN_E_BAD_MODE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!empty) {
-        rc = gvcnn_view_score_fwd(R, W, bias, x, B, V, C, r_layout, dtype, stream);
+        rc = gvcnn_view_score_fwd(R, W, bias, x, nullptr, B, V, C, r_layout, dtype, stream);
         if (rc) return rc;
     }
     rc = batch_score_tail(empty ? nullptr : x, xsum, x_mean, scores, bins, flags, status, B, V, G, multiplier, edge_ulps,

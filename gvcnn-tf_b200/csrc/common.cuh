@@ -308,6 +308,49 @@ __device__ __forceinline__ void mean_of_sum(float (&m)[E], const int n)
     }
 }
 
+// ---- packed float32 pairs (Blackwell: add/mul/fma .f32x2 - two IEEE round-to-nearest results per instruction) ----
+// The instruction-bound variants of the pooling kernels (bf16 data: half the bytes per element, the same float32
+// arithmetic per element) spend most of their issue slots on the accumulator updates acc += fill and
+// acc += w * P_g.  Each component of a packed operation is rounded exactly like its scalar counterpart, so the
+// results stay bit-identical to the oracle's; only the instruction count halves.
+template <int E>
+__device__ __forceinline__ void acc_add_scalar(float (&acc)[E], const float term)  // acc[e] = RN(acc[e] + term)
+{
+    static_assert(E % 2 == 0, "pairs");
+    const float2 t2 = make_float2(term, term);
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+        const float2 a = __fadd2_rn(make_float2(acc[e], acc[e + 1]), t2);
+        acc[e] = a.x;
+        acc[e + 1] = a.y;
+    }
+}
+template <int E>
+__device__ __forceinline__ void acc_add_scaled(float (&acc)[E], const float w, const float (&m)[E])  // acc[e] = RN(acc[e] + RN(w * m[e]))
+{
+    static_assert(E % 2 == 0, "pairs");
+    const float2 w2 = make_float2(w, w);
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+        const float2 p = __fmul2_rn(w2, make_float2(m[e], m[e + 1]));
+        const float2 a = __fadd2_rn(make_float2(acc[e], acc[e + 1]), p);
+        acc[e] = a.x;
+        acc[e + 1] = a.y;
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void vec_add(float (&a)[E], const float (&b)[E])  // a[e] = RN(a[e] + b[e])
+{
+    static_assert(E % 2 == 0, "pairs");
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+        const float2 r = __fadd2_rn(make_float2(a[e], a[e + 1]), make_float2(b[e], b[e + 1]));
+        a[e] = r.x;
+        a[e + 1] = r.y;
+    }
+}
+
 // ---- element packing ---------------------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {
@@ -388,6 +431,29 @@ __device__ __forceinline__ int score_and_bin(float x, float denom, int G, int ed
     return flags;
 }
 
+// A-priori bound on what a DIFFERENT evaluation of the same score could give (another summation order, FMA or no
+// FMA contraction - e.g. TensorFlow's Eigen GEMV instead of this library's warp reduction): every rounded
+// evaluation of x = sum of n_terms products (+ bias) lies within gamma * A of the exact value, A = sum |r_c w_c|
+// + |bias|, gamma = n u / (1 - n u), u = 2^-24 (Higham, Accuracy and Stability of Numerical Algorithms, ch. 3), so two
+// evaluations differ by at most dx = 2 gamma A.  s = |x| / (1 + |x|) is monotone in |x|: the other evaluation's score
+// lies in [s(|x| - dx), s(|x| + dx)], widened by `edge_ulps` ulps for the evaluation of s itself (TF computes
+// sigmoid(log|x|) with Eigen's polynomial approximations).  Returns GVCNN_FLAG_ORDER_EDGE if that interval straddles
+// a bin edge - the views whose group index could legitimately differ from the reference's own float32 run.
+__device__ __forceinline__ int order_edge_flag(float xm, float A, int n_terms, int G, int mult, int edge_ulps)
+{
+    const float nu = (float)n_terms * 5.9604645e-8f;
+    const float dx = 2.0f * (nu / (1.0f - nu)) * A;
+    const float ax = fabsf(xm);
+    if (!(ax < 3.0e38f) || !(dx < 3.0e38f)) return 0;  // inf / NaN: reported through the other flags
+    const float lo = fmaxf(ax - dx, 0.0f), hi = ax + dx;
+    float s_lo = __fdiv_rn(lo, __fadd_rn(1.0f, lo)), s_hi = __fdiv_rn(hi, __fadd_rn(1.0f, hi));
+    const uint32_t bl = __float_as_uint(s_lo), bh = __float_as_uint(s_hi);
+    s_lo = __uint_as_float(bl > (uint32_t)edge_ulps ? bl - edge_ulps : 0u);
+    s_hi = __uint_as_float(bh + edge_ulps);
+    const float fg = (float)(mult > 0 ? mult : G);
+    return ((int)__fmul_rn(s_lo, fg) != (int)__fmul_rn(s_hi, fg)) ? GVCNN_FLAG_ORDER_EDGE : 0;
+}
+
 __device__ __forceinline__ void publish(int flags, int32_t *flag_out, int32_t *status)
 {
     if (flag_out) *flag_out = flags;
@@ -399,7 +465,7 @@ __device__ __forceinline__ void publish(int flags, int32_t *flag_out, int32_t *s
 }
 
 // ---- launchers implemented in the .cu files ----------------------------------
-int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x,
+int launch_view_score(const ViewPtrs &rp, int64_t r_sb, const float *W, const float *bias, float *x, float *xabs,
                       float *scores, int32_t *bins, int32_t *flags, int32_t *status, int B, int V, int C,
                       int G, int dtype, bool aligned16, bool fuse_bin, int edge_ulps, int clamp,
                       cudaStream_t st);
@@ -409,7 +475,7 @@ int launch_gap_score(const ViewPtrs &mp, int64_t m_sb, const float *W, const flo
 int launch_batch_sum_x(const float *x, float *xsum, int B, int V, cudaStream_t st);
 int launch_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
                      int32_t *status, int64_t n, int G, int multiplier, int edge_ulps, int clamp, bool x_is_score,
-                     cudaStream_t st);
+                     const float *xabs, int bound_terms, cudaStream_t st);
 int launch_bins_to_scheme(const int32_t *bins, int32_t *scheme, int rows, int V, int G, cudaStream_t st);
 int launch_scheme_to_bins(const int32_t *scheme, int32_t *bins, int32_t *status, int rows, int V, int G,
                           cudaStream_t st);

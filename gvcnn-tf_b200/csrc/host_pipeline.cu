@@ -196,8 +196,8 @@ int gvcnn_grouping_fusion_host(gvcnn_host_pipeline *pipe, const void *R_host, co
             GVCNN_CK(cudaEventRecord(pipe->ev_in[i], s_in));
             GVCNN_CK(cudaStreamWaitEvent(s_k, pipe->ev_in[i], 0));
             if (err != cudaSuccess) break;
-            krc = gvcnn_view_score_fwd(buf + L.R, W_dev, bias_dev, d_x + (size_t)b0 * V, nb, V, C, GVCNN_LAYOUT_BVD,
-                                       dtype, s_k);
+            krc = gvcnn_view_score_fwd(buf + L.R, W_dev, bias_dev, d_x + (size_t)b0 * V, nullptr, nb, V, C,
+                                       GVCNN_LAYOUT_BVD, dtype, s_k);
             GVCNN_CK(cudaEventRecord(pipe->ev_r[i], s_k));
         }
         if (err == cudaSuccess && krc == 0)

@@ -216,12 +216,11 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
     }
 }
 
-template <typename T, int V>
+template <typename T, int V, int NT = 256>
 static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb, const uint8_t *mask,
                              const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int64_t D, int G, int pool,
                              cudaStream_t st, int gapC = 0, int gapHW = 0)
 {
-    constexpr int NT = 256;
     constexpr int E = Elem<T>::kVec;
     const int64_t td = (int64_t)NT * E;
     const int64_t tiles = (D + td - 1) / td;
@@ -256,7 +255,22 @@ static int launch_bwd_fast_t(const void *dS, const int32_t *bins, int64_t bin_sb
                              const float *weights, int64_t w_sb, const ViewPtrs &gp, int64_t g_sb, int32_t *status, int B, int V, int64_t D, int G,
                              int pool, cudaStream_t st)
 {
-    if (D < 256 * Elem<T>::kVec) return -1000;
+    if (D < 256 * Elem<T>::kVec) {
+        // bf16 at D = 1024: one 128-thread tile per shape (see pool_fwd_ring.cu); anything shorter: generic kernel
+        if constexpr (Elem<T>::kVec == 8) {
+            if (D < 128 * Elem<T>::kVec) return -1000;
+            switch (V) {
+            case 4: return launch_bwd_fast_v<T, 4, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            case 6: return launch_bwd_fast_v<T, 6, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            case 8: return launch_bwd_fast_v<T, 8, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            case 12: return launch_bwd_fast_v<T, 12, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            case 16: return launch_bwd_fast_v<T, 16, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            case 20: return launch_bwd_fast_v<T, 20, 128>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
+            default: return -1000;
+            }
+        }
+        return -1000;
+    }
     switch (V) {
     case 4: return launch_bwd_fast_v<T, 4>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);
     case 6: return launch_bwd_fast_v<T, 6>(dS, bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G, pool, st);

@@ -91,11 +91,25 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
     // and issues that load while thread 0 is still initialising them.  Nothing touches global memory
     // before pdl_wait(); the consumers' first global access (a store) comes after a full barrier, i.e. after
     // the producer's wait, and they wait themselves as well.
-    int nb = 0x7fffffff;
+    // Bins are prefetched kBinAhead tiles ahead into a small register queue: with small tiles (V = 6, bf16, D = 1024:
+    // 12 KB) the producer spends ~0.3 us per tile, less than the L2 latency of a bins load issued only one tile ahead,
+    // and the whole ring then ran at the pace of that load (round 2 sweep: 2.5x the HBM time at that point).
+    constexpr int kBinAhead = 4;
+    int nbq[kBinAhead];
+#pragma unroll
+    for (int j = 0; j < kBinAhead; ++j) nbq[j] = 0x7fffffff;
+    int b_pf = 0, tile_pf = 0;  // coordinates of the tile whose bins are fetched next
     if ((int)threadIdx.x >= NCONS) {
         pdl_wait();
-        if ((int)blockIdx.x < num_tiles && (int)(threadIdx.x & 31) < V)
-            nb = __ldg(bins + (int64_t)b * bin_sb + (threadIdx.x & 31));
+#pragma unroll
+        for (int j = 0; j < kBinAhead; ++j) {
+            const int64_t tj = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+            if (tj < num_tiles && (int)(threadIdx.x & 31) < V)
+                nbq[j] = __ldg(bins + (tj / tiles_per_shape) * bin_sb + (threadIdx.x & 31));
+        }
+        const int64_t tn = (int64_t)blockIdx.x + (int64_t)kBinAhead * gridDim.x;
+        b_pf = (int)(tn / tiles_per_shape);
+        tile_pf = (int)(tn - (int64_t)b_pf * tiles_per_shape);
     }
     __syncthreads();
     pdl_wait();
@@ -109,12 +123,18 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int64_t d0 = (int64_t)tile * TD;
             const uint32_t row_bytes = (uint32_t)min((int64_t)TD, D - d0) * sizeof(T);
-            int bin = nb;
+            int bin = nbq[0];
             if (lane == 0 && t == (int)blockIdx.x) GVCNN_RING_MARK(5);
-            // next tile's coordinates; prefetch its bins behind this tile's work
+            // next tile's coordinates; the bins of the tile kBinAhead steps ahead go in flight behind this tile's work
             int b_n = b + step_b, tile_n = tile + step_t;
             if (tile_n >= tiles_per_shape) { tile_n -= tiles_per_shape; ++b_n; }
-            if (t + (int)gridDim.x < num_tiles && lane < V) nb = __ldg(bins + (int64_t)b_n * bin_sb + lane);
+#pragma unroll
+            for (int j = 0; j + 1 < kBinAhead; ++j) nbq[j] = nbq[j + 1];
+            if ((int64_t)t + (int64_t)kBinAhead * gridDim.x < num_tiles && lane < V)
+                nbq[kBinAhead - 1] = __ldg(bins + (int64_t)b_pf * bin_sb + lane);
+            b_pf += step_b;
+            tile_pf += step_t;
+            if (tile_pf >= tiles_per_shape) { tile_pf -= tiles_per_shape; ++b_pf; }
             if (lane < V && (bin < 0 || bin >= G)) {
                 if (status && tile == 0) atomicAdd(status + GVCNN_STATUS_BIN_RANGE, 1);
                 bin = bin < 0 ? 0 : G - 1;
@@ -280,7 +300,23 @@ static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
     // wide and two CTAs share the SM with two slots each - four independent slots drain and refill more
     // smoothly than two (V = 20: forward 111.7 -> 109.5 us, with tie mask 130.3 -> 126.1 us); for V <= 12 the
     // narrow tiles (four CTAs per SM) measured the same as the wide ones.
-    if (D < 256 * Elem<T>::kVec) return -1000;  // tiles narrower than one consumer row: generic kernel
+    if (D < 256 * Elem<T>::kVec) {
+        // descriptors shorter than one 256-column tile.  bf16 at D = 1024 (a point of the BASELINE sweep) is 128 columns
+        // of 16 bytes: 128-consumer CTAs, narrow slots, deeper ring.  Anything shorter: generic kernel.
+        if constexpr (Elem<T>::kVec == 8) {
+            if (D < 128 * Elem<T>::kVec) return -1000;
+            switch (V) {
+            case 4: return launch_ring_v<T, 4, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 6: return launch_ring_v<T, 6, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 8: return launch_ring_v<T, 8, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 12: return launch_ring_v<T, 12, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 16: return launch_ring_v<T, 16, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 20: return launch_ring_v<T, 20, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            default: return -1000;
+            }
+        }
+        return -1000;
+    }
     switch (V) {
     case 4: return launch_ring_v<T, 4, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
     case 6: return launch_ring_v<T, 6, 256, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);

@@ -101,16 +101,14 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     float m[E];
                     Elem<T>::unpack(make_uint4(m2[0], m2[1], m2[2], m2[3]), m);
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);
-#pragma unroll
-                    for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                    acc_add_scaled(acc, w, m);
                 }
                 if (fill != 0.0f) {
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
                         const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;  // w_g * P_g, P_g = fill
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+                        acc_add_scalar(acc, term);
                     }
                     gcur += (int)nskip;
                 }
@@ -184,16 +182,14 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     }
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);  // acc += w_g * P_g
                     if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, cnt);
-#pragma unroll
-                    for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], __fmul_rn(w, m[e]));
+                    acc_add_scaled(acc, w, m);
                 }
                 if (fill != 0.0f) {  // empty groups in between / after: w = 1 (or given), P = fill
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
                         const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;  // w_g * P_g, P_g = fill
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+                        acc_add_scalar(acc, term);
                     }
                     gcur += (int)nskip;
                 }
@@ -205,9 +201,12 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             } else {
                 float x[E];
                 Elem<T>::unpack(raw[k < V ? k : 0], x);
+                if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
-                for (int e = 0; e < E; ++e)
-                    m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+                    for (int e = 0; e < E; ++e) m[e] = fmaxf(m[e], x[e]);
+                } else {
+                    vec_add(m, x);
+                }
                 ++cnt;
             }
         }

@@ -193,6 +193,14 @@ class ScoreResult:
         """bool tensor: views whose score is within edge_ulps of a bin edge."""
         return (self.flags & C.FLAG_NEAR_EDGE) != 0
 
+    def order_edge(self):
+        """bool tensor: views whose bin another evaluation ORDER of the same float32 dot product (e.g. the
+        reference's own TensorFlow/Eigen GEMV) could legitimately put elsewhere: the a-priori rounding bound
+        |dx| <= 2 gamma_n sum |r_c w_c| carried through s = |x| / (1 + |x|) straddles a bin edge.  A superset of
+        near_edge(); this, not the 1-ulp flag, is the set to exclude when comparing group indices with TensorFlow.
+        (Not computed by the GAP-folded score kernel, whose flags cover the FC's 1-ulp edge only.)"""
+        return (self.flags & (C.FLAG_ORDER_EDGE | C.FLAG_NEAR_EDGE)) != 0
+
 
 # --------------------------------------------------------------------------
 # score + bin                                           nets/model.py:143-148, :23
@@ -268,37 +276,45 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
                                               rv.layout, dt, edge_ulps, int(clamp), _stream()),
                         "gvcnn_score_bin_fwd")
         elif score_reduce == "batch":
-            xb = torch.empty((rv.B, rv.V), dtype=torch.float32, device=dev)
+            # x and (pooled-descriptor input only) A = sum |R W| + |b| per (shape, view); column sums of both in one
+            # [2, V] buffer, so ONE exchange carries them across the ranks; A feeds the a-priori order-sensitivity flag
+            want_bound = HW == 1
+            xb = torch.empty((2 if want_bound else 1, max(rv.B, 1), rv.V), dtype=torch.float32, device=dev)
             if HW > 1:
-                C.check(L.gvcnn_gap_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), None, _ptr(xb), None, None, None, None,
+                C.check(L.gvcnn_gap_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), None, _ptr(xb[0]), None, None, None, None,
                                                   rv.B, rv.V, HW, Craw, 1, rv.layout, dt, 0, 0, 0, _stream()),
                         "gvcnn_gap_score_bin_fwd")
             else:
-                C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb), rv.B, rv.V, rv.D,
+                C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb[0]), _ptr(xb[1]), rv.B, rv.V, rv.D,
                                                rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
-            buf = torch.empty((5, 1, rv.V), dtype=torch.int32, device=dev)
-            xsum, x, scores = (buf[i].view(torch.float32) for i in range(3))
-            bins, flags = buf[3], buf[4]
+            sums = torch.empty((2, rv.V), dtype=torch.float32, device=dev)
+            buf = torch.empty((4, 1, rv.V), dtype=torch.int32, device=dev)
+            x, scores = buf[0].view(torch.float32), buf[1].view(torch.float32)
+            bins, flags = buf[2], buf[3]
             if rv.B > 0:
-                C.check(L.gvcnn_batch_sum_x(_ptr(xb), _ptr(xsum), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
+                for j in range(2 if want_bound else 1):
+                    C.check(L.gvcnn_batch_sum_x(_ptr(xb[j]), _ptr(sums[j]), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
+                if not want_bound:
+                    sums[1].zero_()
             else:
-                xsum.zero_()
+                sums.zero_()
             denom = rv.B if global_count is None else int(global_count)
             if exchange is not None:                                 # a gvcnn_exchange_fn (e.g. parallel.P2PComm)
                 fn, user = exchange
-                C.check(fn(user, _ptr(xsum), rv.V, _stream()), "exchange")
+                C.check(fn(user, _ptr(sums), 2 * rv.V, _stream()), "exchange")
             elif process_group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(xsum, group=process_group)
+                dist.all_reduce(sums, group=process_group)
                 if global_count is None:
                     cnt = torch.tensor([rv.B], dtype=torch.int64, device=dev)
                     dist.all_reduce(cnt, group=process_group)
                     denom = int(cnt.item())
             if denom <= 0:
                 raise ValueError("score_reduce='batch' over an empty (global) batch")
-            C.check(L.gvcnn_score_bin(_ptr(xsum), ctypes.c_float(float(denom)), _ptr(x), _ptr(scores), _ptr(bins),
+            C.check(L.gvcnn_score_bin(_ptr(sums[0]), ctypes.c_float(float(denom)), _ptr(x), _ptr(scores), _ptr(bins),
                                       _ptr(flags), _ptr(status), rv.V, num_group, int(multiplier or 0), edge_ulps,
-                                      int(clamp), _stream()), "gvcnn_score_bin")
+                                      int(clamp), _ptr(sums[1]) if want_bound else None, Craw + 2 + denom, _stream()),
+                    "gvcnn_score_bin")
         else:
             raise ValueError("score_reduce must be 'shape' or 'batch'")
     res = ScoreResult(x, scores, bins, flags, status, num_group)

@@ -12,7 +12,7 @@
  *     name says `host`; the library keeps no mutable global state and allocates
  *     no device memory of its own (the only objects with a lifetime are the
  *     explicit gvcnn_host_pipeline / gvcnn_comm handles the caller creates and
- *     destroys; a gvcnn_comm owns its 1 MB peer-visible receive buffer);
+ *     destroys; a gvcnn_comm owns its 2 MB peer-visible receive buffer);
  *     calls are stream-ordered, asynchronous and re-entrant;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - return value: 0 = ok, < 0 = GVCNN_E_* argument error (nothing was
@@ -81,6 +81,12 @@ extern "C" {
 #define GVCNN_FLAG_NEAR_EDGE 1
 #define GVCNN_FLAG_BIN_RANGE 2
 #define GVCNN_FLAG_NAN 4
+#define GVCNN_FLAG_ORDER_EDGE 8  /* the a-priori rounding-error bound of the FC dot product
+                                    (any summation order / FMA contraction: |dx| <= 2 gamma_n
+                                    sum|r_c w_c|) lets the score cross a bin edge: the group index
+                                    may legitimately differ from another float32 evaluation, e.g.
+                                    the reference's own TensorFlow run.  Per-view flag only (no
+                                    status counter); computed only when `flags` is requested. */
 
 /* argument errors */
 #define GVCNN_E_BAD_ARG (-1)     /* null pointer, non-positive dimension         */
@@ -106,8 +112,10 @@ int gvcnn_check_device(void);
  * x[b, v] = sum_c R[b, v, c] * W[v, c] + bias[v], one warp per (shape, view)
  * row, fixed summation order (see DESIGN.md "score kernel").
  * R: [B,V,C] / [V,B,C] / V pointers (r_layout), dtype f32 or bf16.
- * x: float32 [B, V]. */
-int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x,
+ * x: float32 [B, V].  xabs (nullable): float32 [B, V], sum_c |R W| + |bias| - the
+ * input of the a-priori order-sensitivity report (GVCNN_FLAG_ORDER_EDGE), summed
+ * over the batch with gvcnn_batch_sum_x and handed to gvcnn_score_bin. */
+int gvcnn_view_score_fwd(const void *R, const float *W, const float *bias, float *x, float *xabs,
                          int B, int V, int C, int r_layout, int dtype, void *stream);
 
 /* Deterministic column sums xsum[v] = sum_b x[b, v] (float32 [V]) for the
@@ -128,12 +136,16 @@ int gvcnn_batch_sum_x(const float *x, float *xsum, int B, int V, void *stream);
  * hard-coded `score * 10` of nets/model.py:23 for any num_group (a bin >= G is
  * then the reference's IndexError, reported through flags / status).
  * x_mean (nullable) receives xm.
+ * xabs (nullable; same indexing as x) with bound_terms > 0: also raises
+ * GVCNN_FLAG_ORDER_EDGE where |dx| <= 2 gamma_n (xabs / denom), n = bound_terms
+ * rounded operations (C + 2 per dot product, + the batch size when x is a batch
+ * sum), lets another evaluation order put the score in a different bin.
  * flags (nullable) gets GVCNN_FLAG_* per element; status counts them.
  * clamp != 0 stores min(bin, G-1) instead of the out-of-range value (the
  * flag / status are still raised). */
 int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, int32_t *bins,
                     int32_t *flags, int32_t *status, int64_t n, int G, int multiplier,
-                    int edge_ulps, int clamp, void *stream);
+                    int edge_ulps, int clamp, const float *xabs, int bound_terms, void *stream);
 
 /* gvcnn_view_score_fwd + gvcnn_score_bin(denom = 1) in ONE kernel: the
  * per-shape path (SURVEY.md D5 'shape').  Replaces the device->host->device
@@ -350,7 +362,7 @@ int gvcnn_grouping_fusion_host(gvcnn_host_pipeline *pipe,
  * floats) and the V partial sums of the literal batch mean.  One process per
  * GPU, up to GVCNN_COMM_MAX_WORLD GPUs of one node, vectors of up to
  * GVCNN_COMM_MAX_FLOATS floats.  One kernel per rank: push to every peer's
- * receive buffer (cudaIpc-mapped, NVLink stores), flag, wait, add the K slots
+ * receive buffer (cudaIpc-mapped, NVLink stores of {value, sequence} pairs), poll, add the K slots
  * in rank order (bit-identical result on every rank), scale, in place; no host
  * rendezvous, graph-capturable.
  *   gvcnn_comm_create: allocates this rank's receive buffer on the current

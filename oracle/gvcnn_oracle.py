@@ -39,7 +39,7 @@ __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion",
     "view_scores", "score_from_x", "bins_from_scores", "edge_ulps_distance",
     "pool_fuse_fwd", "pool_fuse_bwd", "grouping_fusion_fwd", "round_bf16",
-    "sorted_view_order", "tie_mask_planes", "gap_mean_kernel_order", "add_n",
+    "sorted_view_order", "tie_mask_planes", "gap_mean_kernel_order", "add_n", "order_edge",
 ]
 
 
@@ -281,6 +281,34 @@ def edge_ulps_distance(s, num_group, k=1):
         hi = np.nextafter(hi, np.float32(np.inf))
     b = bins_from_scores(s, num_group)
     return (bins_from_scores(lo, num_group) != b) | (bins_from_scores(hi, num_group) != b)
+
+
+def order_edge(xm, A, n_terms, num_group, edge_ulps=1, multiplier=None):
+    """The a-priori order-sensitivity report (GVCNN_FLAG_ORDER_EDGE; csrc/common.cuh order_edge_flag), float32 op
+    for op: two rounded evaluations of x = sum of n_terms products lie within dx = 2 gamma_n A of each other
+    (A = sum |r_c w_c| + |b|, gamma_n = n u / (1 - n u), u = 2^-24); True where [s(|x| - dx), s(|x| + dx)], widened
+    by edge_ulps ulps, straddles a bin edge - i.e. where another float32 evaluation order (TensorFlow's) may
+    legitimately produce a different group index."""
+    f = np.float32
+    xm = np.asarray(xm, dtype=np.float32)
+    A = np.asarray(A, dtype=np.float32)
+    nu = f(n_terms) * f(5.9604645e-8)
+    dx = (f(2.0) * (nu / (f(1.0) - nu))) * A
+    ax = np.abs(xm)
+    with np.errstate(invalid="ignore", over="ignore"):
+        ok = (ax < f(3.0e38)) & (dx < f(3.0e38))
+        lo = np.maximum(ax - dx, f(0.0))
+        hi = ax + dx
+        s_lo = (lo / (f(1.0) + lo)).astype(np.float32)
+        s_hi = (hi / (f(1.0) + hi)).astype(np.float32)
+    bl = s_lo.view(np.uint32).astype(np.int64)
+    bh = s_hi.view(np.uint32).astype(np.int64)
+    s_lo = np.where(bl > edge_ulps, bl - edge_ulps, 0).astype(np.uint32).view(np.float32)
+    s_hi = (bh + edge_ulps).astype(np.uint32).view(np.float32)
+    fg = f(multiplier if multiplier else num_group)
+    with np.errstate(invalid="ignore"):
+        out = np.trunc(s_lo * fg) != np.trunc(s_hi * fg)
+    return out & ok
 
 
 # --------------------------------------------------------------------------

@@ -58,7 +58,7 @@ sp = [ctypes.c_void_p(main.cuda_stream)]
 
 K = {
     "score": lambda i: C.check(L.gvcnn_score_bin_fwd(p(Rs[i % NS]), p(W), p(bias), None, p(scores[i % NS]), p(bins[i % NS]), None, p(status), B, V, Cr, G, 0, dt, 0, 1, sp[0]), "score"),
-    "score_x": lambda i: C.check(L.gvcnn_view_score_fwd(p(Rs[i % NS]), p(W), p(bias_lit), p(xs[i % NS]), B, V, Cr, 0, dt, sp[0]), "score_x"),
+    "score_x": lambda i: C.check(L.gvcnn_view_score_fwd(p(Rs[i % NS]), p(W), p(bias_lit), p(xs[i % NS]), None, B, V, Cr, 0, dt, sp[0]), "score_x"),
     "pool": lambda i: C.check(L.gvcnn_pool_fuse_fwd(p(Fs[i % NS]), p(bins[i % NS]), V, None, 0, p(Ss[i % NS]), None, None, p(status), B, V, D, G, pool, fill, 0, dt, sp[0]), "pool"),
     "pool_mask": lambda i: C.check(L.gvcnn_pool_fuse_fwd(p(Fs[i % NS]), p(bins[i % NS]), V, None, 0, p(Ss[i % NS]), None, p(masks[i % NS]), p(status), B, V, D, G, pool, fill, 0, dt, sp[0]), "pool_mask"),
     "bwd": lambda i: C.check(L.gvcnn_pool_fuse_bwd(p(dSs[i % NS]), p(bins[i % NS]), V, None, 0, p(masks[i % NS]), p(dFs[i % NS]), p(status), B, V, D, G, pool, 0, dt, sp[0]), "bwd"),

@@ -84,7 +84,7 @@ def test_argument_errors_before_any_launch(cabi):
                                         0, 0, 4, None, None, 2, p, 1 << 20) == -1
     assert L.gvcnn_grouping_fusion_host(None, p, p, p, p, p, None, None, None, None, None, 4, 12, 64, 64, 8, 0, 1.0,
                                         0, 5, 4, None, None, 2, p, 1 << 20) == -8
-    assert L.gvcnn_score_bin(p, 1.0, None, p, p, None, None, 12, 8, -1, 0, 0, None) == -1      # negative multiplier
+    assert L.gvcnn_score_bin(p, 1.0, None, p, p, None, None, 12, 8, -1, 0, 0, None, 0, None) == -1      # negative multiplier
     if not torch.cuda.is_available():
         assert L.gvcnn_check_device() == -7            # no CPU fallback: the library says so
 

@@ -257,6 +257,39 @@ def test_fused_descriptor_within_tolerance_of_both_add_n_orders(model, G, pool, 
     assert np.any(S != tf8)                     # the orders really differ at these group counts
 
 
+@pytest.mark.parametrize("B,V,Cr,G", [(2048, 12, 1024, 8), (512, 6, 1024, 10), (256, 20, 1000, 16), (300, 12, 512, 10)])
+def test_order_edge_flag_covers_every_other_evaluation_order(model, c_oracle, B, V, Cr, G):
+    """What can differ from the reference's own TensorFlow run is the float32 summation ORDER of the Dense(1) dot
+    product.  GVCNN_FLAG_ORDER_EDGE marks every view whose bin the a-priori rounding bound allows to differ:
+    (1) the flag equals the oracle's restatement of the bound bit for bit; (2) every view whose bin differs under
+    another evaluation order - plain left-to-right float32, a pairwise float32 tree, exact float64 - is flagged;
+    (3) the flagged set stays small."""
+    R, W, b = score_inputs(B * 7 + V, B, V, Cr, bias_range=0.5)
+    sr = model.score_bin(dev(R), dev(W), dev(b), G, edge_ulps=1, clamp=True, check=False)
+    flags = sr.flags.cpu().numpy()
+    E = 4 if Cr % 4 == 0 else 1
+    xk = c_oracle.view_score_x_kernel_order(R, W, b, E=E)
+    A = c_oracle.view_score_x_kernel_order(np.abs(R), np.abs(W), np.abs(b), E=E)      # same order, absolute values
+    want = O.order_edge(xk, A, Cr + 2, G, edge_ulps=1)
+    np.testing.assert_array_equal((flags & 8) != 0, want)
+    covered = sr.order_edge().cpu().numpy()
+    bins = sr.bins.cpu().numpy()
+    # other evaluation orders of the same float32 data
+    x_l2r, _ = O.view_scores(R, W, b, dtype=np.float32)
+    prod = (R * W[None]).astype(np.float32)
+    while prod.shape[2] > 1:                                                           # pairwise tree
+        if prod.shape[2] % 2:
+            prod = np.concatenate([prod, np.zeros(prod.shape[:2] + (1,), np.float32)], axis=2)
+        prod = prod[:, :, 0::2] + prod[:, :, 1::2]
+    x_tree = prod[:, :, 0] + b[None]
+    x64, _ = O.view_scores(R, W, b, dtype=np.float64)
+    for other in (x_l2r, x_tree, x64.astype(np.float32)):
+        ob = O.bins_from_scores(O.score_from_x_rational(other.astype(np.float32)), G)
+        ob = np.minimum(ob, G - 1)
+        assert np.all((ob == bins) | covered), "a bin that differs under another summation order is not flagged"
+    assert covered.mean() < 0.08
+
+
 # ---------------------------------------------------------------- GAP in front of the score FC (nets/model.py:144)
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("B,V,h,w,Cr,G", [(4, 6, 10, 10, 1024, 10), (8, 6, 8, 8, 1024, 10), (3, 12, 10, 10, 512, 8),
@@ -306,7 +339,8 @@ def test_gap_folded_into_the_score_kernel(model, c_oracle, dtype, B, V, h, w, Cr
     np.testing.assert_array_equal(bi.cpu().numpy(), O.bins_from_scores(sk, G))
     if dtype == "f32":      # ... which for float32 maps is exactly gvcnn_score_bin_fwd on the pooled descriptor
         sr = model.score_bin(dev(R_want), Wd, bd, G, edge_ulps=1)
-        assert torch.equal(x, sr.x) and torch.equal(sc, sr.scores) and torch.equal(bi, sr.bins) and torch.equal(fl, sr.flags)
+        assert torch.equal(x, sr.x) and torch.equal(sc, sr.scores) and torch.equal(bi, sr.bins)
+        assert torch.equal(fl, sr.flags & ~8)       # the GAP-folded kernel does not compute the a-priori ORDER_EDGE report
     # the Python mirror takes the maps wherever it takes pooled descriptors: list of V [N, h, w, C] (the reference's
     # end_points['resnet_v2_50/block3'] per view), per-shape and per-batch scores
     views = [md[:, v].contiguous() for v in range(V)]
