@@ -572,7 +572,7 @@ def run_cuda_arm(args):
         return model.grouping_fusion(Rd, Wd, bias_lit, Fd, G, score_reduce="batch", clamp=True, exchange=ex_model,
                                      process_group=pg, global_count=global_count)[0]
 
-    def api_refseq(i):
+    def api_refseq(i, check=True):
         # names and argument order of train.py:270-288 + nets/model.py:154-157
         Rd = sets[i % NSETS][1]
         if world > 1:
@@ -582,7 +582,7 @@ def run_cuda_arm(args):
             scores = sr.scores
         else:
             scores = model.view_scores(Rd, Wd, bias_lit)
-        scheme = model.group_scheme([scores[0]], G, V)
+        scheme = model.group_scheme([scores[0]], G, V, check=check)
         w = model.group_weight(scheme)
         desc = model.view_pooling(view_lists[i % NSETS], scheme)
         return model.group_fusion(desc, w)
@@ -591,10 +591,13 @@ def run_cuda_arm(args):
     with torch.no_grad():
         for name, fn in (("grouping_fusion(score_reduce='shape')", api_shape),
                          ("grouping_fusion(score_reduce='batch')", api_batch),
-                         ("view_scores -> group_scheme -> group_weight -> view_pooling -> group_fusion", api_refseq)):
+                         ("view_scores -> group_scheme -> group_weight -> view_pooling -> group_fusion", api_refseq),
+                         ("the same sequence, group_scheme(check='deferred'): exceptions raised one call late, no "
+                          "synchronisation inside the step", lambda i: api_refseq(i, "deferred"))):
             for i in range(3):
                 fn(i)
             api[name] = timed_wall(fn, K) / K
+    model.check_deferred(dev)
     # the reference-shaped sequence gives the one-call literal path's bits
     with torch.no_grad():
         S_seq = api_refseq(0)

@@ -35,30 +35,52 @@ def needs_build():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """defines / out: A/B builds of the same sources with -D flags into another path (scripts/_build/)."""
+    """Compiles every source to an object file in parallel (one nvcc per file), then links the shared library.
+    defines / out: A/B builds of the same sources with -D flags into another path (scripts/_build/)."""
     if out is None and not force and not needs_build():
         return SO
-    cmd = [
-        nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-fmad=false",                      # one rounding per float32 op unless fmaf() is written
-        "-Xcompiler", "-fPIC", "-shared",
-        "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", out or SO,
-    ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
+    import concurrent.futures
+    import hashlib
+    import tempfile
+    target = out or SO
+    common = [nvcc_path()]
+    if os.path.exists("/usr/bin/g++"):      # the image's $CC/$CXX wrappers are not what nvcc should use as host compiler
+        common += ["-ccbin", "/usr/bin/g++"]
+    common += ["-std=c++17", "-O3", "-lineinfo",
+               "-gencode", "arch=compute_100a,code=sm_100a",
+               "-fmad=false",                      # one rounding per float32 op unless fmaf() is written
+               "-Xcompiler", "-fPIC",
+               "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ["-D" + d for d in defines]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
-    # the image's $CC/$CXX wrappers are not what nvcc should use as host compiler
-    if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        common.insert(1, "-Xptxas=-v")
+    tag = hashlib.sha1((" ".join(defines) + target).encode()).hexdigest()[:10]
+    objdir = os.path.join(tempfile.gettempdir(), "gvcnn_build_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run(common + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, res
+
+    log = []
+    objs = []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        for src, obj, res in ex.map(compile_one, SOURCES):
+            log.append(res.stdout + res.stderr)
+            if res.returncode != 0:
+                sys.stderr.write("".join(log))
+                raise RuntimeError("nvcc failed compiling %s" % src)
+            objs.append(obj)
+    link = common[:1] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + \
+        ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", target] + objs
+    res = subprocess.run(link, capture_output=True, text=True)
+    log.append(res.stdout + res.stderr)
     if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libgvcnn_sm100.so")
+        sys.stderr.write("".join(log))
+        raise RuntimeError("nvcc failed linking libgvcnn_sm100.so")
     if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
-    return out or SO
+        sys.stderr.write("".join(log))
+    return target
 
 
 if __name__ == "__main__":

@@ -328,11 +328,14 @@ __device__ __forceinline__ void acc_add_scalar(float (&acc)[E], const float term
 template <int E>
 __device__ __forceinline__ void acc_add_scaled(float (&acc)[E], const float w, const float (&m)[E])  // acc[e] = RN(acc[e] + RN(w * m[e]))
 {
+    // The products stay SCALAR multiplies: ptxas (12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2 into one
+    // FFMA2 even under -fmad=false - one rounding instead of two, 1-ulp differences from the reference's op order in
+    // 11 % of the elements (caught by test_group_fusion_custom_weights_with_empty_fill).  Scalar mul.rn is never
+    // contracted; tests/test_cabi_host.py::test_no_packed_fma_in_the_library checks the SASS for FFMA2.
     static_assert(E % 2 == 0, "pairs");
-    const float2 w2 = make_float2(w, w);
 #pragma unroll
     for (int e = 0; e < E; e += 2) {
-        const float2 p = __fmul2_rn(w2, make_float2(m[e], m[e + 1]));
+        const float2 p = make_float2(__fmul_rn(w, m[e]), __fmul_rn(w, m[e + 1]));
         const float2 a = __fadd2_rn(make_float2(acc[e], acc[e + 1]), p);
         acc[e] = a.x;
         acc[e + 1] = a.y;

@@ -136,7 +136,10 @@ __device__ __forceinline__ float transpose_reduce4(const float (&acc)[4], const 
 // pipeline, four rows per butterfly.  The launcher picks rpw so that the whole grid is ONE resident wave (see
 // launch_view_score_t): with 4 rows per warp the grid was 2.59 waves of 592 resident CTAs and the last, 59 % full
 // wave left the memory system under-used for a third of the kernel (ncu: DRAM 69.6 %, profiles/r01z_ncu_full.md).
-template <typename T, int NB, bool FUSE_BIN, bool BOUND>  // NB = 16-byte loads per lane per row = C / (32 * E)
+// The x-only form (literal batch mode) and the fused form (x -> score -> bin) are ONE kernel - `scores` null or
+// not - on purpose: as two template instantiations ptxas scheduled them differently and the x-only one ran 7 us
+// slower for the same loads (38.7 vs 31.5 us at B = 4096, V = 12).
+template <typename T, int NB, bool BOUND>  // NB = 16-byte loads per lane per row = C / (32 * E)
 __global__ void __launch_bounds__(kScoreWarps * 32)
 view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__restrict__ W,
                        const float *__restrict__ bias, float *__restrict__ x_out, float *__restrict__ xabs_out,
@@ -158,7 +161,6 @@ view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__res
     const T *__restrict__ r0 = reinterpret_cast<const T *>(rp.p[v]) + lane * E;
     const float *__restrict__ w = W + (int64_t)v * C + lane * E;
     const float bv = __ldg(bias + v);
-
     // PD rows of loads in flight per warp (16 x 16 bytes per lane whatever the row length): a 2 KB bf16 row needs four
     // rows ahead to cover the DRAM latency at full bandwidth, a 4 KB float32 row two
 #ifndef GVCNN_SCORE_PD_MAX
@@ -222,8 +224,10 @@ view_score_fast_kernel(const ViewPtrs rp, const int64_t r_sb, const float *__res
             const float x = __fadd_rn(k, bv);
             const float A = BOUND ? __fadd_rn(ka, fabsf(bv)) : 0.0f;
             if (x_out) x_out[row] = x;
-            if constexpr (BOUND && !FUSE_BIN) xabs_out[row] = A;
-            if constexpr (FUSE_BIN) {
+            if constexpr (BOUND) {
+                if (xabs_out) xabs_out[row] = A;
+            }
+            if (scores) {
                 float s;
                 int bin;
                 int flags = score_and_bin(x, 1.0f, G, edge_ulps, clamp, s, bin);
@@ -389,26 +393,22 @@ static int launch_view_score_t(const ViewPtrs &rp, int64_t r_sb, const float *W,
         // warps per SM -> 16 rows per warp, 384 CTAs on 444 slots.
         static const int env_rpw = env_int_once("GVCNN_SCORE_RPW", 0);  // A/B knob: 4 = one butterfly per warp (round 1)
         const dim3 fblock(kScoreWarps * 32);
-#define GVCNN_LAUNCH_FAST(NB_, FUSE_, BOUND_)                                                                \
+#define GVCNN_LAUNCH_FAST(NB_, BOUND_)                                                                       \
     do {                                                                                                     \
         const int64_t warp_slots = (int64_t)score_sm_count() *                                               \
-            resident_ctas<view_score_fast_kernel<T, NB_, FUSE_, BOUND_>>(kScoreWarps * 32) * kScoreWarps;    \
+            resident_ctas<view_score_fast_kernel<T, NB_, BOUND_>>(kScoreWarps * 32) * kScoreWarps;           \
         int rpw = (int)(kFastRows * ((rows + kFastRows * warp_slots - 1) / (kFastRows * warp_slots)));       \
         if (env_rpw >= kFastRows && env_rpw % kFastRows == 0) rpw = env_rpw;                                 \
         const int64_t items = (int64_t)V * ((B + rpw - 1) / rpw);                                            \
         const dim3 fgrid((unsigned)((items + kScoreWarps - 1) / kScoreWarps));                               \
-        err = launch_pdl(view_score_fast_kernel<T, NB_, FUSE_, BOUND_>, fgrid, fblock, 0, st, rp, r_sb, W, bias, x, \
-                         xabs, scores, bins, flags, status, B, V, G, edge_ulps, clamp, items, rpw);          \
+        err = launch_pdl(view_score_fast_kernel<T, NB_, BOUND_>, fgrid, fblock, 0, st, rp, r_sb, W, bias, x, \
+                         xabs, fuse_bin ? scores : nullptr, bins, flags, status, B, V, G, edge_ulps, clamp, items, rpw); \
     } while (0)
-#define GVCNN_LAUNCH_FAST_B(NB_, FUSE_)                                                                      \
+#define GVCNN_LAUNCH_FAST_B(NB_)                                                                             \
     do {                                                                                                     \
-        if (bound) GVCNN_LAUNCH_FAST(NB_, FUSE_, true); else GVCNN_LAUNCH_FAST(NB_, FUSE_, false);           \
+        if (bound) GVCNN_LAUNCH_FAST(NB_, true); else GVCNN_LAUNCH_FAST(NB_, false);                         \
     } while (0)
-        if (C == 8 * 32 * Elem<T>::kVec) {
-            if (fuse_bin) GVCNN_LAUNCH_FAST_B(8, true); else GVCNN_LAUNCH_FAST_B(8, false);
-        } else {
-            if (fuse_bin) GVCNN_LAUNCH_FAST_B(4, true); else GVCNN_LAUNCH_FAST_B(4, false);
-        }
+        if (C == 8 * 32 * Elem<T>::kVec) GVCNN_LAUNCH_FAST_B(8); else GVCNN_LAUNCH_FAST_B(4);
 #undef GVCNN_LAUNCH_FAST_B
 #undef GVCNN_LAUNCH_FAST
         if (err != cudaSuccess) return (int)err;

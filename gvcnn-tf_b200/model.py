@@ -30,7 +30,7 @@ __all__ = [
     "group_scheme", "group_weight", "view_pooling", "group_fusion", "view_scores",
     "score_bin", "pool_fuse", "grouping_fusion", "GroupDescriptors", "ScoreResult",
     "GVCNNHead", "gvcnn_head", "basic_pool", "raise_for_status", "grouping_fusion_paper", "pool_fuse_gap",
-    "make_exchange",
+    "make_exchange", "check_deferred",
 ]
 
 _POOL = {"max": C.POOL_MAX, "mean": C.POOL_MEAN}
@@ -278,7 +278,7 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
         elif score_reduce == "batch":
             # x and (pooled-descriptor input only) A = sum |R W| + |b| per (shape, view); column sums of both in one
             # [2, V] buffer, so ONE exchange carries them across the ranks; A feeds the a-priori order-sensitivity flag
-            want_bound = HW == 1
+            want_bound = HW == 1 and edge_ulps > 0                   # view_scores() asks for scores only
             xb = torch.empty((2 if want_bound else 1, max(rv.B, 1), rv.V), dtype=torch.float32, device=dev)
             if HW > 1:
                 C.check(L.gvcnn_gap_score_bin_fwd(rv.arg, _ptr(Wc), _ptr(bc), None, _ptr(xb[0]), None, None, None, None,
@@ -349,16 +349,71 @@ def _tag_of(t):
     return tag if (tag is not None and tag["version"] == t._version) else None
 
 
+class _DeferredStatus:
+    """check='deferred': the reference's IndexError / ValueError without a device synchronisation in the middle of
+    the step.  The status counters accumulate in one persistent device tensor per device; after every call its 16
+    bytes are copied to pinned host memory asynchronously, and the NEXT call (or ``check_deferred()``) raises if the
+    last completed copy shows a count - CUDA's own error model: reported at a later call, never lost."""
+    _per_device = {}
+
+    def __init__(self, dev):
+        self.status = _new_status(dev)
+        self.host = torch.zeros(C.STATUS_WORDS, dtype=torch.int32).pin_memory()
+        self.event = None
+        self.num_group = 0
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        if key not in cls._per_device:
+            cls._per_device[key] = cls(dev)
+        return cls._per_device[key]
+
+    def poll(self, wait=False):
+        if self.event is None:
+            return
+        if wait:
+            self.event.synchronize()
+        elif not self.event.query():
+            return
+        self.event = None
+        if int(self.host.sum()) != 0:
+            st = self.host.clone()
+            self.host.zero_()
+            self.status.zero_()
+            raise_for_status(st, self.num_group)
+
+    def submit(self, num_group):
+        self.num_group = num_group
+        self.host.copy_(self.status, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+
+def check_deferred(device=None):
+    """Waits for the outstanding deferred status copy (check='deferred') and raises what it reports."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _DeferredStatus.get(dev).poll(wait=True)
+
+
 def _bins_from_scores(scores2d: torch.Tensor, num_group: int, clamp=False, check=True, multiplier=None):
     L = C.lib()
     dev = scores2d.device
-    status = _new_status(dev) if check else None
+    deferred = None
+    if check == "deferred":
+        deferred = _DeferredStatus.get(dev)
+        deferred.poll()
+        status = deferred.status
+    else:
+        status = _new_status(dev) if check else None
     bins = torch.empty(scores2d.shape, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         C.check(L.gvcnn_bins_from_scores(_ptr(scores2d), _ptr(bins), None, _ptr(status), scores2d.numel(),
-                                         num_group, int(multiplier or 0), 0, int(clamp), _stream()),
-                "gvcnn_bins_from_scores")
-    if check:
+                                         num_group, int(multiplier or 0), 0, int(clamp or deferred is not None),
+                                         _stream()), "gvcnn_bins_from_scores")
+        if deferred is not None:
+            deferred.submit(num_group)
+    if check is True:
         raise_for_status(status, num_group)
     return bins
 
@@ -371,7 +426,9 @@ def group_scheme(view_discrimination_score, num_group, num_views, multiplier=Non
     tensor [1, V]; a CUDA tensor [B, V] with B > 1 gives per-shape schemes
     [B, num_group, V].  Returns an int32 CUDA tensor [num_group, num_views].
     Raises IndexError when a score maps to bin >= num_group (score == 1.0) and
-    ValueError on NaN, like the reference (one 16-byte device->host read; check=False skips it).
+    ValueError on NaN, like the reference (one 16-byte device->host read, i.e. a synchronisation in the middle of
+    the step - the reference's own host hop; check=False skips it, check='deferred' keeps the exceptions but
+    raises them at the NEXT call / ``check_deferred()`` from an asynchronous copy, out-of-range bins clamped meanwhile).
     multiplier: the reference hard-codes ``score * 10`` (model.py:23) and only ever runs num_group == 10;
     None generalises that to ``* num_group`` (identical at 10), ``multiplier=10`` is the literal code for any
     num_group (bins >= num_group then raise IndexError exactly like the reference's out-of-bounds write).
@@ -403,7 +460,7 @@ def group_scheme(view_discrimination_score, num_group, num_views, multiplier=Non
         C.check(C.lib().gvcnn_bins_to_scheme(_ptr(bins), _ptr(scheme), rows, num_views, num_group, _stream()),
                 "gvcnn_bins_to_scheme")
     out = scheme[0] if rows == 1 else scheme
-    return _tag(out, kind="scheme", bins=bins, G=num_group, checked=bool(check))
+    return _tag(out, kind="scheme", bins=bins, G=num_group, checked=bool(check))  # one-hot by construction
 
 
 def _small_to_device(x, device, dtype, name):

@@ -123,3 +123,17 @@ def test_product_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "libgvcnn_oracle" not in src, fn
+
+
+def test_no_packed_fma_in_the_library(cabi):
+    """ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, which breaks the
+    one-rounding-per-op contract the bit-exact parity rests on.  The kernels therefore use packed ADDS only
+    (FADD2, csrc/common.cuh); no FFMA2 may appear in the built library, while FADD2 must (the packed path is live)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", cabi.SO_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert sass.count("FFMA2") == 0
+    assert sass.count("FADD2") > 100
