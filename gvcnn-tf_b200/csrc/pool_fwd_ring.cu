@@ -303,13 +303,18 @@ static int launch_ring_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, 
     if (D < 256 * Elem<T>::kVec) {
         // descriptors shorter than one 256-column tile.  bf16 at D = 1024 (a point of the BASELINE sweep) is 128 columns
         // of 16 bytes: 128-consumer CTAs, narrow slots, deeper ring.  Anything shorter: generic kernel.
+#ifndef GVCNN_NARROW_MINB
+#define GVCNN_NARROW_MINB 4  // CTAs per SM of the narrow (128-consumer) ring for V <= 12: with 12-24 KB tiles two CTAs
+                             // (8 consumer warps, 2 producers per SM) left the SM idle between tiles; bf16 V = 6,
+                             // D = 1024: 19.3 -> 14.2 us, V = 12 mean: 46.6 -> 30.2 us (A/B builds: -DGVCNN_NARROW_MINB=2)
+#endif
         if constexpr (Elem<T>::kVec == 8) {
             if (D < 128 * Elem<T>::kVec) return -1000;
             switch (V) {
-            case 4: return launch_ring_v<T, 4, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
-            case 6: return launch_ring_v<T, 6, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
-            case 8: return launch_ring_v<T, 8, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
-            case 12: return launch_ring_v<T, 12, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 4: return launch_ring_v<T, 4, 128, GVCNN_NARROW_MINB>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 6: return launch_ring_v<T, 6, 128, GVCNN_NARROW_MINB>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 8: return launch_ring_v<T, 8, 128, GVCNN_NARROW_MINB>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
+            case 12: return launch_ring_v<T, 12, 128, GVCNN_NARROW_MINB>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
             case 16: return launch_ring_v<T, 16, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
             case 20: return launch_ring_v<T, 20, 128, 2>(fp, f_sb, bins, bin_sb, weights, w_sb, S, mask, status, B, D, G, pool, fill, st);
             default: return -1000;

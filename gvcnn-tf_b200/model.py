@@ -285,8 +285,8 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
                                                   rv.B, rv.V, HW, Craw, 1, rv.layout, dt, 0, 0, 0, _stream()),
                         "gvcnn_gap_score_bin_fwd")
             else:
-                C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb[0]), _ptr(xb[1]), rv.B, rv.V, rv.D,
-                                               rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
+                C.check(L.gvcnn_view_score_fwd(rv.arg, _ptr(Wc), _ptr(bc), _ptr(xb[0]), _ptr(xb[1]) if want_bound else None,
+                                               rv.B, rv.V, rv.D, rv.layout, dt, _stream()), "gvcnn_view_score_fwd")
             sums = torch.empty((2, rv.V), dtype=torch.float32, device=dev)
             buf = torch.empty((4, 1, rv.V), dtype=torch.int32, device=dev)
             x, scores = buf[0].view(torch.float32), buf[1].view(torch.float32)
@@ -1120,20 +1120,24 @@ class _PaperModeFn(torch.autograd.Function):
     No reference counterpart - checked against float64 autograd of the same formulas."""
 
     @staticmethod
-    def forward(ctx, W, b, G, pool, f_layout, r_layout, n_r, *tensors):
+    def forward(ctx, W, b, G, pool, f_layout, r_layout, n_r, status, *tensors):
         L = C.lib()
         r_t, f_t = tensors[:n_r], tensors[n_r:]
         rv = _Views(list(r_t) if r_layout == "list" else r_t[0], None if r_layout == "list" else r_layout, "R")
         fv = _Views(list(f_t) if f_layout == "list" else f_t[0], None if f_layout == "list" else f_layout, "F")
+        # no synchronisation in the training step: out-of-range / NaN scores are clamped for pooling and counted
+        # into the caller's persistent `status` tensor (checked every N steps), as in grouping_fusion
         sr = score_bin(list(r_t) if r_layout == "list" else r_t[0], W, b, G, score_reduce="shape",
-                       layout=None if r_layout == "list" else r_layout, edge_ulps=1, clamp=False, check=True)
+                       layout=None if r_layout == "list" else r_layout, edge_ulps=1, clamp=True, check=False,
+                       status=status)
         dev = fv.device
         weights = torch.empty((rv.B, G), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             C.check(L.gvcnn_group_weight_from_scores(_ptr(sr.scores), _ptr(sr.bins), _ptr(weights), rv.B, rv.V, G,
                                                      _stream()), "gvcnn_group_weight_from_scores")
         S, mask, _, _, bins_c, bstride, w_c, wstride = _pool_fuse_fwd(fv, sr.bins, G, pool, 0.0, weights,
-                                                                      want_mask=True, want_groups=False)
+                                                                      want_mask=True, want_groups=False,
+                                                                      want_status=False)
         ctx.rv, ctx.fv, ctx.G, ctx.pool = rv, fv, G, pool
         ctx.bstride, ctx.wstride = bstride, wstride
         ctx.need_dr = any(t.requires_grad for t in r_t)
@@ -1152,12 +1156,14 @@ class _PaperModeFn(torch.autograd.Function):
         dS2 = dS.reshape(fv.B, fv.D).contiguous()
         dev = dS2.device
         dF = _pool_fuse_bwd(dS2, fv, bins_c, ctx.bstride, w_c, ctx.wstride, mask, G, pool)
-        dweights = torch.empty((fv.B, G), dtype=torch.float32, device=dev)
-        dx = torch.empty((fv.B, fv.V), dtype=torch.float32, device=dev)
-        dW = torch.empty_like(W)
-        dbias = torch.empty(rv.V, dtype=torch.float32, device=dev)
         ws_bytes = L.gvcnn_view_score_bwd_workspace_bytes(rv.V, rv.D)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        n_dw, n_dx, n_W = fv.B * G, fv.B * fv.V, W.numel()
+        scratch = torch.empty(n_dw + n_dx + n_W + rv.V + (ws_bytes + 3) // 4, dtype=torch.float32, device=dev)  # one allocation
+        dweights = scratch[:n_dw].view(fv.B, G)
+        dx = scratch[n_dw:n_dw + n_dx].view(fv.B, fv.V)
+        dW = scratch[n_dw + n_dx:n_dw + n_dx + n_W].view_as(W)
+        dbias = scratch[n_dw + n_dx + n_W:n_dw + n_dx + n_W + rv.V]
+        ws = scratch[n_dw + n_dx + n_W + rv.V:]
         dR_out, dR_views = (rv.empty_like() if ctx.need_dr else (None, None))
         with torch.cuda.device(dev):
             C.check(L.gvcnn_pool_fuse_bwd_weights(fv.arg, _ptr(dS2), _ptr(S), _ptr(bins_c), ctx.bstride, _ptr(w_c),
@@ -1175,10 +1181,11 @@ class _PaperModeFn(torch.autograd.Function):
         else:
             gr = tuple(dR_out) if isinstance(dR_out, list) else (dR_out,)
         gf = tuple(dF) if isinstance(dF, list) else (dF,)
-        return (dW, dbias, None, None, None, None, None) + gr + gf
+        return (dW, dbias, None, None, None, None, None, None) + gr + gf
 
 
-def grouping_fusion_paper(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max", layout=None):
+def grouping_fusion_paper(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max", layout=None,
+                          status=None):
     """Paper-mode grouping + fusion: group weight = mean discrimination score of the group's views, empty
     groups vanish; differentiable w.r.t. the view descriptors AND the score FC (W, b, optionally the raw
     descriptors).  Returns (shape_descriptor, scores, bins, weights).  Per-shape scores/bins."""
@@ -1191,7 +1198,7 @@ def grouping_fusion_paper(raw_view_descriptors, W, b, final_view_descriptors, nu
     else:
         f_t, f_lay = (final_view_descriptors,), (layout or "bvd")
     _require_cuda(W, "W"), _require_cuda(b, "b")
-    return _PaperModeFn.apply(W, b, num_group, pool, f_lay, r_lay, len(r_t), *r_t, *f_t)
+    return _PaperModeFn.apply(W, b, num_group, pool, f_lay, r_lay, len(r_t), status, *r_t, *f_t)
 
 
 class GVCNNHead(torch.nn.Module):
@@ -1233,7 +1240,8 @@ class GVCNNHead(torch.nn.Module):
             return sr.scores, net, self.classifier(net.to(self.classifier.weight.dtype))
         if self.weight_mode == "score":
             S, scores, _, _ = grouping_fusion_paper(raw_view_descriptors, self.score_kernel, self.score_bias,
-                                                    final_view_descriptors, self.num_group, pool=self.pool)
+                                                    final_view_descriptors, self.num_group, pool=self.pool,
+                                                    status=status)
         else:
             S, sr = grouping_fusion(raw_view_descriptors, self.score_kernel.detach(), self.score_bias.detach(),
                                     final_view_descriptors, self.num_group, pool=self.pool,
