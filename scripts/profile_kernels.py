@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Launches each kernel of the path a few times at BASELINE configs[1] size, for ncu.
 
-    ncu --set full --clock-control none --import-source on -k regex:'pool_fuse|view_score' \
-        -s 8 -c 8 -o gpurun_out/prof python scripts/profile_kernels.py
-Order per round: view_score (fused bin), pool_fuse_fwd (no mask), pool_fuse_fwd (mask), pool_fuse_bwd.
+    ncu --set full --clock-control none --import-source on -k regex:'pool_fuse|view_score|batch_mean|gap_score' \
+        -s 14 -c 7 -o gpurun_out/prof python scripts/profile_kernels.py
+Order per round (7 kernels): view_score (fused bin), pool_fuse_fwd (no mask), pool_fuse_fwd (mask), pool_fuse_bwd, then the
+literal batch-mode forward = view_score (x only), batch_mean_bin_fused, pool_fuse_fwd (one shared bin row); --gap adds
+gap_score (N=128, V=6, 10x10x1024 maps) as an 8th.
 """
 import ctypes
 import os
@@ -44,5 +46,21 @@ for _ in range(rounds):
                                   ctypes.c_float(1.0), C.LAYOUT_BVD, dt, sp), "fwd+mask")
     C.check(L.gvcnn_pool_fuse_bwd(p(dS), p(bins), V, None, 0, p(mask), p(dF), p(status), B, V, D, G, pool,
                                   C.LAYOUT_BVD, dt, sp), "bwd")
+    xb = torch.empty(B, V, device=dev)
+    xsum = torch.empty(V, device=dev)
+    sc1 = torch.empty(V, device=dev)
+    bins1 = torch.empty(V, dtype=torch.int32, device=dev)
+    bl = (torch.rand(V, device=dev) * 8 - 4)
+    C.check(L.gvcnn_grouping_fusion_batch_fwd(p(R), p(W), p(bl), p(F), p(xb), p(xsum), None, p(sc1), p(bins1), None, p(S), None,
+                                              p(status), B, V, Cr, D, G, 0, pool, ctypes.c_float(1.0), C.LAYOUT_BVD,
+                                              C.LAYOUT_BVD, dt, 0, 1, B, None, None, sp), "batch fwd")
+    if "--gap" in sys.argv:
+        N2, V2, HW = 128, 6, 100
+        maps = torch.randn(N2, V2, HW, Cr, device=dev).to(dtype)
+        W2 = W[:V2].contiguous()
+        s2 = torch.empty(N2, V2, device=dev)
+        b2 = torch.empty(N2, V2, dtype=torch.int32, device=dev)
+        C.check(L.gvcnn_gap_score_bin_fwd(p(maps), p(W2), p(b), None, None, p(s2), p(b2), None, p(status), N2, V2, HW, Cr, 10,
+                                          C.LAYOUT_BVD, dt, 1, 0, 1, sp), "gap score")
 torch.cuda.synchronize()
 print("profiled", rounds, "rounds; status", status.tolist())
