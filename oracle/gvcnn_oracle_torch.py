@@ -107,8 +107,9 @@ def reference_step_cpu(F_views, R, W, b, num_group, pool="max", empty_fill=1.0):
     G = num_group
     V = len(F_views)
     scheme = torch.zeros((G, V), dtype=torch.int64)
-    for idx, score in enumerate(s.tolist()):
-        scheme[min(int(torch.tensor(score, dtype=torch.float32) * G), G - 1), idx] = 1
+    for idx, score in enumerate(s.reshape(-1).tolist()):
+        # nets/model.py:23 - an out-of-range bin raises IndexError (score == 1.0), a NaN score ValueError; no clamp
+        scheme[int(torch.tensor(score, dtype=torch.float32) * G), idx] = 1
     w = torch.zeros(G, dtype=torch.float32)
     for i in range(G):
         w[i] = 1 + int(scheme[i].sum())

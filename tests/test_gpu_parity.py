@@ -1362,3 +1362,42 @@ def test_seeded_fuzz_against_oracle(model, c_oracle):
         else:
             got = np.stack([t.grad.float().cpu().numpy() for t in x], axis=1)
         np.testing.assert_array_equal(got, wantg, err_msg=tag)
+
+
+def test_p2p_comm_single_rank(model):
+    """gvcnn_comm on one GPU (world size 1): create / all-reduce / error word / destroy through the C ABI - the
+    protocol degenerates to push-to-self, poll, scale.  The multi-rank behaviour (exact rank-order sums, identical on
+    every rank, graph replay, latency vs NCCL) is checked by scripts/comm_check.py under torchrun
+    (profiles/r02e_comm_check_n2.json, r02h_comm_check_n8.json)."""
+    import ctypes
+    from gvcnn_tf_b200 import _cabi as Cb
+    L = Cb.lib()
+    comm = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * Cb.COMM_HANDLE_BYTES)()
+    assert L.gvcnn_comm_create(ctypes.byref(comm), 0, 1, handle) == 0
+    try:
+        assert any(handle)                                         # a real IPC handle came back
+        assert L.gvcnn_comm_connect(comm, bytes(handle)) == 0
+        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for n in (1, 12, 2049, 12300, 16384):
+            x = torch.randn(n, device="cuda")
+            want = x.clone()
+            for _ in range(3):                                     # both phases of the double buffer, and reuse
+                assert L.gvcnn_comm_allreduce_f32(comm, ctypes.c_void_p(x.data_ptr()), n, sp) == 0
+            assert torch.equal(x, want)
+            assert L.gvcnn_comm_allreduce_scaled_f32(comm, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_float(0.25), sp) == 0
+            assert torch.equal(x, want * 0.25)
+        assert L.gvcnn_comm_allreduce_f32(comm, None, 4, sp) == -1
+        assert L.gvcnn_comm_allreduce_f32(comm, ctypes.c_void_p(x.data_ptr()), Cb.COMM_MAX_FLOATS + 1, sp) == -1
+        assert L.gvcnn_comm_error(comm) == 0
+        # the literal forward with the communicator as its exchange: one rank, so the fused kernel's no-comm form runs
+        B, V, D, G, Cr = 64, 12, 1024, 8, 256
+        F, _, _ = make_inputs(5, B, V, D, G)
+        R, W, b = score_inputs(6, B, V, Cr, bias_range=3.0)
+        fn = ctypes.cast(L.gvcnn_comm_allreduce_f32, ctypes.c_void_p)
+        S1, sr1 = model.grouping_fusion(dev(R), dev(W), dev(b), dev(F), G, score_reduce="batch", exchange=(fn, comm),
+                                        global_count=B, clamp=True)
+        S2, sr2 = model.grouping_fusion(dev(R), dev(W), dev(b), dev(F), G, score_reduce="batch", clamp=True)
+        assert torch.equal(S1, S2) and torch.equal(sr1.bins, sr2.bins)
+    finally:
+        assert L.gvcnn_comm_destroy(comm) == 0
