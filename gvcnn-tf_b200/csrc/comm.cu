@@ -60,19 +60,43 @@ allreduce_oneshot_kernel(const CommPeers peers, const int rank, const int world,
             ll_store2(dst, v[0], v[1], seq);
             ll_store2(dst + 2, v[2], v[3], seq);
         }
-        // ---- wait + reduce in rank order (identical on every rank), scale, store in place
+        // ---- wait + reduce in rank order (identical on every rank), scale, store in place.  All K slots are polled
+        // in ONE pass of independent loads per round (the first version polled rank after rank: 2 K dependent L2 round
+        // trips, 6 us of the 14.6 us a 49 KB exchange took between 8 GPUs)
         const unsigned long long t0 = comm_timer_ns();
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        unsigned long long w[kCommMaxWorld][4];
         bool ok = true;
-        for (int r = 0; r < world; ++r) {
-            const uint2 *src = &mine->ll[phase][r][lo + i];
-            float t[4];
-            ok = ok && ll_wait2(src, seq, t[0], t[1], t0) && ll_wait2(src + 2, seq, t[2], t[3], t0);
-            if (!ok) break;
-            if (r == 0) {
-                for (int j = 0; j < 4; ++j) acc[j] = t[j];
-            } else {
-                for (int j = 0; j < 4; ++j) acc[j] = __fadd_rn(acc[j], t[j]);
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int r = 0; r < kCommMaxWorld; ++r) {
+                if (r < world) {
+                    const uint2 *src = &mine->ll[phase][r][lo + i];
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[r][0]), "=l"(w[r][1]) : "l"(src) : "memory");
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[r][2]), "=l"(w[r][3]) : "l"(src + 2) : "memory");
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kCommMaxWorld; ++r) {
+                if (r < world) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) all = all && ((uint32_t)(w[r][j] >> 32) == seq);
+                }
+            }
+            if (all) break;
+            if (comm_timer_ns() - t0 > kCommTimeoutNs) {
+                ok = false;
+                break;
+            }
+        }
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __uint_as_float((uint32_t)w[0][j]);
+#pragma unroll
+        for (int r = 1; r < kCommMaxWorld; ++r) {
+            if (r < world) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float((uint32_t)w[r][j]));
             }
         }
         if (!ok) atomicExch(&mine->error, 1u);

@@ -1201,6 +1201,14 @@ def grouping_fusion_paper(raw_view_descriptors, W, b, final_view_descriptors, nu
     return _PaperModeFn.apply(W, b, num_group, pool, f_lay, r_lay, len(r_t), status, *r_t, *f_t)
 
 
+def _spatial_mean(S):
+    """GlobalAveragePooling2D of the fused map [N, h, w, C] -> [N, C] (nets/model.py:163) for the un-folded path;
+    an empty batch (a rank whose shard is exhausted) stays empty."""
+    if S.dim() <= 2:
+        return S
+    return S.reshape(S.shape[0], int(math.prod(S.shape[1:-1])), S.shape[-1]).mean(dim=1)
+
+
 class GVCNNHead(torch.nn.Module):
     """The trainable state of the path: V separate Dense(1) score layers
     (Keras defaults: glorot-uniform kernel, zero bias; nets/model.py:145 sits
@@ -1249,7 +1257,7 @@ class GVCNNHead(torch.nn.Module):
                                     process_group=process_group, check=check, status=status,
                                     global_count=global_count)
             scores = sr.scores
-        net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
+        net = _spatial_mean(S)
         logits = self.classifier(net.to(self.classifier.weight.dtype))
         return scores, S, logits
 
@@ -1266,5 +1274,5 @@ def gvcnn_head(raw_view_descriptors, final_view_descriptors, head: GVCNNHead, gr
     desc = view_pooling(final_view_descriptors, group_scheme, pool=head.pool, empty_fill=head.empty_fill)
     w = group_weight if group_weight is not None else globals()["group_weight"](group_scheme)
     S = group_fusion(desc, w)
-    net = S.reshape(S.shape[0], -1, S.shape[-1]).mean(dim=1) if S.dim() > 2 else S
+    net = _spatial_mean(S)
     return scores, S, head.classifier(net.to(head.classifier.weight.dtype))

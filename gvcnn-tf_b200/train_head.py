@@ -99,6 +99,51 @@ class SyntheticFeatures:
         return (self.raw[:0].to(self.device), self.final[:0].to(self.device), self.labels[:0].to(self.device))
 
 
+class _BucketOverlap:
+    """Overlaps the flat gradient all-reduce with the rest of the backward pass.  In the reference-literal mode the
+    only parameters with a gradient are the classifier's (the score FC gets none), and autograd produces
+    them FIRST - before the pooling/fusion backward kernel that dominates the step.  A post-accumulate hook on each
+    parameter counts the gradients in; when the last expected one has arrived the bucket is packed and the all-reduce
+    (the library's one-kernel NVLink all-reduce, or NCCL) is launched on its own stream, while the dF kernel still runs
+    on the main one; join() orders the optimizer step behind it."""
+
+    def __init__(self, head, bucket, comm, world):
+        self.bucket, self.comm, self.world = bucket, comm, world
+        self.stream = torch.cuda.Stream(priority=-1)
+        self.fired, self.work, self.pending = False, None, 0
+        self.expected = [p for p in bucket.params if p.requires_grad]
+        literal = getattr(head, "weight_mode", "count") == "count"
+        # parameters that receive a gradient in this mode (the score FC only in paper mode)
+        self.with_grad = [p for n, p in head.named_parameters()
+                          if p.requires_grad and not (literal and n in ("score_kernel", "score_bias"))]
+        for p in self.with_grad:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def reset(self):
+        self.fired, self.work, self.pending = False, None, len(self.with_grad)
+
+    def _hook(self, _param):
+        self.pending -= 1
+        if self.pending == 0 and not self.fired:
+            self.launch()
+
+    def launch(self):
+        self.fired = True
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.bucket.pack()
+            if self.comm is not None:
+                self.comm.all_reduce_(self.bucket.flat, 1.0 / self.world, stream=self.stream)   # sum * 1/K, one kernel
+            else:
+                self.work = self.bucket.all_reduce_mean(async_op=True)
+
+    def join(self):
+        if self.work is not None:
+            with torch.cuda.stream(self.stream):
+                self.bucket.finish(self.work)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 def confusion_matrix(labels, preds, n):
     cm = torch.zeros((n, n), dtype=torch.int64)
     for t, p in zip(labels.tolist(), preds.tolist()):
@@ -148,6 +193,8 @@ def main(argv=None):
                 comm.close()
                 comm = None
 
+    overlap = _BucketOverlap(head, bucket, comm, world) if bucket is not None else None
+
     start_epoch, global_step = 0, 0
     if flags.saved_checkpoint_dir:                  # train.py:229-234: restore the latest checkpoint
         cks = sorted(f for f in os.listdir(flags.saved_checkpoint_dir) if f.startswith(flags.ckpt_name_to_save))
@@ -180,6 +227,8 @@ def main(argv=None):
             for gparam in opt.param_groups:
                 gparam["lr"] = lr
             opt.zero_grad(set_to_none=True)
+            if overlap is not None:
+                overlap.reset()
             if len(y) > 0 or (world > 1 and flags.score_reduce == "batch"):
                 # literal mode on a sharded batch: every rank bins the same GLOBAL batch mean
                 _, _, logits = head(raw, final, process_group=pg if flags.score_reduce == "batch" else None,
@@ -191,11 +240,9 @@ def main(argv=None):
                 tot_loss += float(loss.detach()) * len(y)
                 n_seen += len(y)
             if bucket is not None:                  # one flat all-reduce (utils/_train_helper.py:17-31)
-                bucket.pack()
-                if comm is not None:
-                    comm.all_reduce_(bucket.flat, 1.0 / world)      # sum * 1/K, one kernel, stream ordered
-                else:
-                    bucket.finish(bucket.all_reduce_mean(async_op=True))
+                if not overlap.fired:               # no backward ran on this rank (empty batch): zeros into the sum
+                    overlap.launch()
+                overlap.join()
                 bucket.unpack()
             opt.step()
             global_step += 1
@@ -219,6 +266,7 @@ def main(argv=None):
                        os.path.join(flags.train_logdir, "%s-%04d" % (flags.ckpt_name_to_save, epoch)))
     if rank == 0 and history:
         print("confusion matrix (last epoch):\n%s" % cm)
+    main.last_head = head                              # for callers / checks that want the trained module
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
