@@ -56,15 +56,24 @@ def test_algorithmic_bytes_match_baseline_md():
 
 
 def test_committed_cuda_arm_line_has_the_contract_keys():
-    """The CUDA arm cannot run here; the line it printed on the B200 box (profiles/r01z_bench_n1.json) is checked
-    against the contract instead, so a change of bench.py's keys without a re-measurement is caught."""
-    with open(os.path.join(ROOT, "profiles", "r01z_bench_n1.json")) as f:
-        line = json.load(f)
+    """The CUDA arm cannot run here; the line it printed on the B200 box (profiles/r02p_bench_n1.json) is checked
+    against the contract instead, so a change of bench.py's keys without a re-measurement is caught - and against the
+    reference arm's line from the same box (profiles/r02p_bench_reference.json): same config object, like for like."""
+    with open(os.path.join(ROOT, "profiles", "r02p_bench_n1.json")) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    with open(os.path.join(ROOT, "profiles", "r02p_bench_reference.json")) as f:
+        ref = json.loads(f.read().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+                "shape_mode", "fwd_bwd", "api", "sweep", "config0"):
         assert key in line, key
     assert line["n_gpus"] == 1 and line["unit"] == "shapes/s" and line["dtype"] == "f32" and line["vs_baseline"] is None
-    assert line["gpu_launches"] == 2 * line["steps"] and "workload" in line["config"] and "l2" in line["config"]
+    assert line["gpu_launches"] == 3 * line["steps"] and "workload" in line["config"] and "l2" in line["config"]
+    assert ref["impl"] == "reference" and ref["config"] == line["config"] and ref["metric"] == line["metric"]
+    assert line["config"]["score_reduce"] == "batch" and line["config"]["B_per_gpu"] == 4096
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.bench_config(1, "weak")
     r = line["roofline"]
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in r, key
@@ -75,5 +84,8 @@ def test_committed_cuda_arm_line_has_the_contract_keys():
     e = line["e2e"]
     assert e["h2d_bytes_per_step"] == 4096 * 12 * (1024 + 2048) * 4 and e["d2h_bytes_per_step"] > 0
     assert 0 < e["value"] < line["value"]                                     # host copies are inside the e2e region
+    assert 0.5 < e["frac"] <= 1.05 and e["h2d_peak_gbs"] > 0                  # against the link's measured peak
+    assert e["host_path_bits_equal_device_path"] is True
+    assert line["api"]["reference_sequence_bits_equal_one_call_path"] is True
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
