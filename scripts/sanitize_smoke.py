@@ -36,6 +36,50 @@ for B, V, D, G, dt, pool in cases:
     _ = model.group_fusion(desc, torch.rand(G, device=dev) + 0.5)
     sb = model.score_bin(R, W, b + 1.0, G, score_reduce="batch")
     torch.cuda.synchronize()
+    # round 2: the literal forward in one call (fused batch-mean kernel), custom weights with the ones dummy on the
+    # ring's weights instantiation, a plain dict through group_fusion, the literal multiplier
+    S1, sr1 = model.grouping_fusion(R, W, b + 1.0, F.detach(), G, pool=pool, score_reduce="batch", clamp=True)
+    _ = model.pool_fuse(F.detach(), sr.bins.clamp(0, G - 1), G, pool=pool, group_weight=torch.rand(G, device=dev) + 0.5)
+    _ = model.group_fusion({g: F.detach()[:, g % V] for g in range(min(G, 6))}, torch.rand(G, device=dev) + 0.5)
+    _ = model.group_scheme(sr.scores[:1] * 0.5, max(G, 10), V, multiplier=10)
+    torch.cuda.synchronize()
+# round 2: GAP of the raw maps folded into the score kernel (fp32 and bf16, per-shape and batch, odd HW)
+for dt in (torch.float32, torch.bfloat16):
+    maps = torch.randn(3, 6, 7, 1024, device=dev).to(dt)
+    W6 = (torch.rand(6, 1024, device=dev) * 2 - 1) * 0.0765
+    b6 = torch.zeros(6, device=dev)
+    _ = model.score_bin(maps, W6, b6, 10, clamp=True, check=False)
+    _ = model.score_bin([maps[:, v].reshape(3, 7, 1, 1024) for v in range(6)], W6, b6 + 1.0, 10, score_reduce="batch", clamp=True)
+    torch.cuda.synchronize()
+# round 2: one-rank communicator (push to self, poll, scale) and the host-buffer entry point in both modes
+import ctypes  # noqa: E402
+from gvcnn_tf_b200 import _cabi as C  # noqa: E402
+L = C.lib()
+comm = ctypes.c_void_p()
+handle = (ctypes.c_ubyte * C.COMM_HANDLE_BYTES)()
+C.check(L.gvcnn_comm_create(ctypes.byref(comm), 0, 1, handle), "comm_create")
+C.check(L.gvcnn_comm_connect(comm, bytes(handle)), "comm_connect")
+x = torch.randn(12300, device=dev)
+for _ in range(3):
+    C.check(L.gvcnn_comm_allreduce_scaled_f32(comm, ctypes.c_void_p(x.data_ptr()), x.numel(), ctypes.c_float(0.5),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "allreduce")
+torch.cuda.synchronize()
+C.check(L.gvcnn_comm_error(comm), "comm_error")
+L.gvcnn_comm_destroy(comm)
+Bh, Vh, Dh, Gh, Ch = 300, 12, 1024, 8, 256
+Fh, Rh = torch.randn(Bh, Vh, Dh).pin_memory(), torch.randn(Bh, Vh, Ch).pin_memory()
+Sh = torch.empty(Bh, Dh).pin_memory()
+Wh, bh = (torch.rand(Vh, Ch, device=dev) - 0.5), torch.zeros(Vh, device=dev) + 1.0
+pipe = ctypes.c_void_p()
+C.check(L.gvcnn_host_pipeline_create(ctypes.byref(pipe), 2), "pipeline_create")
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+for mode in (0, 1):
+    nbytes = L.gvcnn_host_workspace_bytes(Bh, 128, Vh, Ch, Dh, C.F32, 0, mode)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    C.check(L.gvcnn_grouping_fusion_host(pipe, p(Rh), p(Fh), p(Wh), p(bh), p(Sh), None, None, None, None, None, Bh, Vh, Ch,
+                                         Dh, Gh, C.POOL_MAX, ctypes.c_float(1.0), C.F32, mode, Bh, None, None, 128, p(ws),
+                                         nbytes), "host")
+L.gvcnn_host_pipeline_destroy(pipe)
 # GAP-folded pooling (real geometry, small)
 Fm = [torch.relu(torch.randn(3, 5, 5, 2048, device=dev)).requires_grad_(True) for _ in range(6)]
 out = model.pool_fuse_gap(Fm, torch.randint(0, 10, (3, 6), dtype=torch.int32, device=dev), 10)
