@@ -58,6 +58,11 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
     constexpr int P = (V + 7) / 8;
     constexpr uint32_t kRowStride = ROWSTRIDE;
     constexpr bool kPackedMax = (E == 8) && (POOL == GVCNN_POOL_MAX);  // bf16 max pooling
+#ifndef GVCNN_MEAN_CHUNKED
+#define GVCNN_MEAN_CHUNKED 1  // A/B builds: 0 = fully unrolled mean walk for every V (round 1)
+#endif
+    // bf16 only: float32 mean at V = 20 is HBM-bound either way and measured 4 % slower chunked (135.8 vs 129.9 us)
+    constexpr bool kChunkedMean = GVCNN_MEAN_CHUNKED && (POOL == GVCNN_POOL_MEAN) && (V % 4 == 0) && V >= 12 && E == 8;
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.0f;
     // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
@@ -152,6 +157,66 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                 const uint32_t w1 = __byte_perm(src[2], src[3], sel);
                 *reinterpret_cast<uint2 *>(mask + ((int64_t)p * B) * D + out_off) = make_uint2(w0, w1);
             }
+        }
+    } else if (active && kChunkedMean) {
+        // Mean pooling with many views: the sorted rows are walked four at a time - an outer loop that is NOT
+        // unrolled around a body that is - with the next four rows' loads in flight.  The fully unrolled walk below
+        // replicates the group-close code (mean_of_sum's three cases + the weighted add + the fill loop) V + 1 times:
+        // 113 KB of SASS at V = 20 bf16, and ncu shows the consumers starving on instruction fetch (stall
+        // no_instruction 2.6 per issue, instruction-cache hit rate 65 %, profiles/r02r_ncu_bf16_v20_mean.md).  Here it
+        // exists five times.  Same operations in the same order as the unrolled walk.  bf16 V = 20, D = 2048: 125.1 ->
+        // 96.9 us; D = 1024: 55.6 -> 43.5 us; V = 12: 27.5 -> 25.6 us (profiles/r02s_mean_chunked_ab.jsonl).
+        if constexpr (kChunkedMean) {
+        constexpr int CH = 4;
+        float m[E];
+        int cnt = 0, gcur = 0;
+        uint4 nxt[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) nxt[j] = *reinterpret_cast<const uint4 *>(col + j * kRowStride);
+        auto close_group = [&](const int k) {  // acc += w_g * mean of the group that ended before sorted position k
+            const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);
+            mean_of_sum(m, cnt);
+            acc_add_scaled(acc, w, m);
+        };
+        auto fill_empty = [&](const uint32_t nskip) {
+            if (fill != 0.0f) {
+#pragma unroll 1
+                for (uint32_t q = 0; q < nskip; ++q) {
+                    const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;
+                    acc_add_scalar(acc, term);
+                }
+                gcur += (int)nskip;
+            }
+        };
+#pragma unroll 1
+        for (int k0 = 0; k0 < V; k0 += CH) {
+            uint4 cur[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
+            if (k0 + CH < V) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) nxt[j] = *reinterpret_cast<const uint4 *>(col + (k0 + CH + j) * kRowStride);
+            }
+            const uint32_t fmc = fm >> k0;                                                       // uniform
+            const uint32_t skc = reinterpret_cast<const uint32_t *>(plan_s.skip)[k0 >> 2];       // uniform (broadcast)
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if ((k0 + j == 0) || ((fmc >> j) & 1u)) {  // uniform: a group ends / starts here
+                    if (k0 + j > 0) close_group(k0 + j);
+                    fill_empty((skc >> (8 * j)) & 0xffu);
+                    Elem<T>::unpack(cur[j], m);
+                    cnt = 1;
+                    ++gcur;
+                } else {
+                    float x[E];
+                    Elem<T>::unpack(cur[j], x);
+                    vec_add(m, x);
+                    ++cnt;
+                }
+            }
+        }
+        close_group(V);
+        fill_empty(tail_skip);
         }
     } else if (active) {
         // all V rows of this thread's column, in bin order, fetched in one batch

@@ -37,19 +37,43 @@ class P2PComm:
         self.world = dist.get_world_size(group)
         if self.world > C.COMM_MAX_WORLD:
             raise ValueError("P2PComm: at most %d ranks (one node)" % C.COMM_MAX_WORLD)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        have_cuda = torch.cuda.is_available()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if have_cuda else torch.device("cpu")
+        self.device = torch.device(device)
         self._h = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * C.COMM_HANDLE_BYTES)()
-        with torch.cuda.device(self.device):
-            C.check(self._L.gvcnn_comm_create(ctypes.byref(self._h), self.rank, self.world, handle), "gvcnn_comm_create")
-            mine = torch.tensor(list(handle), dtype=torch.uint8)
-            if dist.get_backend(group) == "nccl":
+        on_gpu = dist.get_backend(group) == "nccl"
+        # Construction is COLLECTIVE and fails on every rank or on none: a rank whose buffer / IPC mapping cannot be
+        # set up still takes part in both exchanges below, so no rank is left waiting in a collective the others skipped.
+        err = None
+        import contextlib
+        with (torch.cuda.device(self.device) if have_cuda else contextlib.nullcontext()):
+            try:
+                C.check(self._L.gvcnn_comm_create(ctypes.byref(self._h), self.rank, self.world, handle), "gvcnn_comm_create")
+            except Exception as e:                                   # noqa: BLE001
+                err = e
+            mine = torch.tensor(list(handle) + [0 if err is None else 1], dtype=torch.uint8)
+            if on_gpu:
                 mine = mine.to(self.device)
             allh = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(allh, mine, group=group)
-            blob = bytes(torch.cat([t.cpu() for t in allh]).tolist())
-            C.check(self._L.gvcnn_comm_connect(self._h, blob), "gvcnn_comm_connect")
-        dist.barrier(group)                                          # every rank has mapped every peer's buffer
+            table = torch.stack([t.cpu() for t in allh])
+            if int(table[:, -1].sum()) != 0 and err is None:
+                err = RuntimeError("gvcnn_comm_create failed on another rank")
+            if err is None:
+                try:
+                    C.check(self._L.gvcnn_comm_connect(self._h, bytes(table[:, :-1].reshape(-1).tolist())), "gvcnn_comm_connect")
+                except Exception as e:                               # noqa: BLE001
+                    err = e
+            ok = torch.tensor([0 if err is None else 1], dtype=torch.int32)
+            if on_gpu:
+                ok = ok.to(self.device)
+            dist.all_reduce(ok, group=group)                         # also the barrier: every rank has mapped every peer
+            if int(ok.item()) != 0:
+                self.close()
+                raise RuntimeError("P2PComm could not be set up on every rank: %s"
+                                   % (err if err is not None else "peer mapping failed on another rank"))
         # (function, user pointer) in the gvcnn_exchange_fn form the library's entry points take
         self.exchange = (self._L.gvcnn_comm_allreduce_f32, self._h)
         self.exchange_c = (ctypes.cast(self._L.gvcnn_comm_allreduce_f32, ctypes.c_void_p), self._h)

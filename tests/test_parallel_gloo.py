@@ -54,6 +54,15 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(100 + rank)
+        # --- P2PComm construction is collective: without a GPU it must fail on EVERY rank, after both of its
+        #     exchanges, instead of leaving a rank waiting in a collective the others skipped
+        try:
+            parallel.P2PComm()
+            raise AssertionError("P2PComm must not come up without a CUDA device")
+        except RuntimeError as e:
+            assert "could not be set up on every rank" in str(e), str(e)
+        dist.barrier()
+
         # --- init broadcast (utils/_train_helper.py:66-94)
         lin = torch.nn.Linear(5, 3)
         parallel.broadcast_parameters(lin, src=0)
