@@ -1368,7 +1368,7 @@ def test_p2p_comm_single_rank(model):
     """gvcnn_comm on one GPU (world size 1): create / all-reduce / error word / destroy through the C ABI - the
     protocol degenerates to push-to-self, poll, scale.  The multi-rank behaviour (exact rank-order sums, identical on
     every rank, graph replay, latency vs NCCL) is checked by scripts/comm_check.py under torchrun
-    (profiles/r02e_comm_check_n2.json, r02h_comm_check_n8.json)."""
+    (profiles/r02e_comm_check_n2.json, r02w_comm_check_n8.json)."""
     import ctypes
     from gvcnn_tf_b200 import _cabi as Cb
     L = Cb.lib()
