@@ -171,6 +171,21 @@ int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, i
                             xabs, bound_terms, static_cast<cudaStream_t>(stream));
 }
 
+// column sums + [exchange] + mean / score / bin for the literal batch mode, in one launch when it can be (score.cu)
+int gvcnn_batch_mean_bin(const float *x, float *xsum, float *x_mean, float *scores, int32_t *bins, int32_t *flags,
+                         int32_t *status, int B, int V, int G, int multiplier, int edge_ulps, int clamp,
+                         int64_t global_count, gvcnn_exchange_fn exchange, void *exchange_user, void *stream)
+{
+    if (B < 0 || V <= 0 || G <= 0 || multiplier < 0 || edge_ulps < 0) return GVCNN_E_BAD_ARG;
+    if ((B > 0 && !x) || !xsum || !bins) return GVCNN_E_BAD_ARG;
+    if (V > GVCNN_MAX_VIEWS) return GVCNN_E_TOO_MANY_VIEWS;
+    if (G > GVCNN_MAX_GROUPS) return GVCNN_E_TOO_MANY_GROUPS;
+    if (global_count < B || global_count <= 0) return GVCNN_E_BAD_ARG;
+    if (B == 0 && !exchange) return GVCNN_E_BAD_ARG;  // a mean over nothing
+    return batch_score_tail(B > 0 ? x : nullptr, xsum, x_mean, scores, bins, flags, status, B, V, G, multiplier, edge_ulps,
+                            clamp, global_count, exchange, exchange_user, static_cast<cudaStream_t>(stream));
+}
+
 int gvcnn_bins_from_scores(const float *scores, int32_t *bins, int32_t *flags, int32_t *status, int64_t n,
                            int G, int multiplier, int edge_ulps, int clamp, void *stream)
 {

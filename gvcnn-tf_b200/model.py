@@ -74,12 +74,41 @@ def make_exchange(process_group):
 # --------------------------------------------------------------------------
 # plumbing
 # --------------------------------------------------------------------------
-def _stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+# The helpers below sit on every call into the library; they are written for low overhead (the reference-shaped
+# five-call sequence is bound by Python time, not GPU time: bench.py `api`).
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream():
+    """cudaStream_t of torch's current stream on the current device, as the integer ctypes passes for a void*."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device()) or None
+    return torch.cuda.current_stream().cuda_stream or None
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Device pointer as a plain int (ctypes converts it for a c_void_p parameter); None stays a null pointer."""
+    return None if t is None else (t.data_ptr() or None)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def _on(dev):
+    """`with _on(dev):` - switch the current CUDA device only if it is not already `dev` (torch.cuda.device costs two
+    driver calls even when it has nothing to do)."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(dev)
 
 
 def _dtype_code(dt: torch.dtype) -> int:
@@ -106,23 +135,28 @@ class _Views:
         if isinstance(x, (list, tuple)):                      # the reference's Python list of views
             if len(x) == 0:
                 raise ValueError("%s: empty view list" % name)
-            for t in x:
-                _require_cuda(t, name)
             first = x[0]
-            views = []
-            for t in x:
-                if t.shape != first.shape or t.dtype != first.dtype or t.device != first.device:
-                    raise ValueError("%s: all views must share shape, dtype and device" % name)
-                views.append(t if t.is_contiguous() else t.contiguous())
+            _require_cuda(first, name)
+            shape, dt, dv = first.shape, first.dtype, first.device
+            views, ptrs = [], []
+            for t in x:                                       # one pass: checks, contiguity, pointer table
+                if t is not first:
+                    _require_cuda(t, name)
+                    if t.shape != shape or t.dtype != dt or t.device != dv:
+                        raise ValueError("%s: all views must share shape, dtype and device" % name)
+                if not t.is_contiguous():
+                    t = t.contiguous()
+                views.append(t)
+                ptrs.append(t.data_ptr())
             self.keep = views
             self.V = len(views)
-            self.B = first.shape[0] if first.dim() > 0 else 1
-            self.D = int(math.prod(first.shape[1:])) if first.dim() > 0 else 1
-            self.view_shape = tuple(first.shape)
-            self.dtype, self.device = first.dtype, first.device
+            self.B = shape[0] if len(shape) > 0 else 1
+            self.D = int(math.prod(shape[1:])) if len(shape) > 0 else 1
+            self.view_shape = tuple(shape)
+            self.dtype, self.device = dt, dv
             self.layout = C.LAYOUT_PTRS
-            self.table = (ctypes.c_void_p * self.V)(*[t.data_ptr() for t in views])
-            self.arg = ctypes.cast(self.table, ctypes.c_void_p)
+            self.table = (ctypes.c_void_p * self.V)(*ptrs)
+            self.arg = ctypes.addressof(self.table)
             self.kind = "list"
         else:
             _require_cuda(x, name)
@@ -142,7 +176,7 @@ class _Views:
             self.D = int(math.prod(t.shape[2:]))
             self.view_shape = (self.B,) + tuple(t.shape[2:])
             self.dtype, self.device = t.dtype, t.device
-            self.arg = ctypes.c_void_p(t.data_ptr())
+            self.arg = t.data_ptr() or None
             self.kind = layout
             self.tensor = t
         if self.V <= 0 or self.D <= 0:          # B == 0 (an empty batch) is fine: nothing is launched
@@ -260,7 +294,7 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
     if status is None and check:
         status = _new_status(dev)
     dt = _dtype_code(rv.dtype)
-    with torch.cuda.device(dev):
+    with _on(dev):
         if score_reduce == "shape":
             if multiplier not in (None, num_group):
                 raise ValueError("multiplier is only selectable with score_reduce='batch' or through group_scheme")
@@ -291,20 +325,35 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
             buf = torch.empty((4, 1, rv.V), dtype=torch.int32, device=dev)
             x, scores = buf[0].view(torch.float32), buf[1].view(torch.float32)
             bins, flags = buf[2], buf[3]
+            if not want_bound and process_group is None:
+                # no order-sensitivity report asked for: column sums + [exchange] + mean / score / bin in ONE call
+                denom = rv.B if global_count is None else int(global_count)
+                if denom <= 0:
+                    raise ValueError("score_reduce='batch' over an empty (global) batch")
+                fn, user = (None, None)
+                if exchange is not None:
+                    fn, user = exchange
+                    fn = ctypes.cast(fn, ctypes.c_void_p) if not isinstance(fn, (int, ctypes.c_void_p)) else fn
+                C.check(L.gvcnn_batch_mean_bin(_ptr(xb[0]), _ptr(sums[0]), _ptr(x), _ptr(scores), _ptr(bins), _ptr(flags),
+                                               _ptr(status), rv.B, rv.V, num_group, int(multiplier or 0), edge_ulps,
+                                               int(clamp), denom, fn, user, _stream()), "gvcnn_batch_mean_bin")
+                res = ScoreResult(x, scores, bins, flags, status, num_group)
+                if check:
+                    res.check()
+                return res
+            nsum = 2 if want_bound else 1                            # rows of `sums` in use: sum x (and sum A)
             if rv.B > 0:
-                for j in range(2 if want_bound else 1):
+                for j in range(nsum):
                     C.check(L.gvcnn_batch_sum_x(_ptr(xb[j]), _ptr(sums[j]), rv.B, rv.V, _stream()), "gvcnn_batch_sum_x")
-                if not want_bound:
-                    sums[1].zero_()
             else:
                 sums.zero_()
             denom = rv.B if global_count is None else int(global_count)
             if exchange is not None:                                 # a gvcnn_exchange_fn (e.g. parallel.P2PComm)
                 fn, user = exchange
-                C.check(fn(user, _ptr(sums), 2 * rv.V, _stream()), "exchange")
+                C.check(fn(user, _ptr(sums), nsum * rv.V, _stream()), "exchange")
             elif process_group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(sums, group=process_group)
+                dist.all_reduce(sums[:nsum], group=process_group)
                 if global_count is None:
                     cnt = torch.tensor([rv.B], dtype=torch.int64, device=dev)
                     dist.all_reduce(cnt, group=process_group)
@@ -407,7 +456,7 @@ def _bins_from_scores(scores2d: torch.Tensor, num_group: int, clamp=False, check
     else:
         status = _new_status(dev) if check else None
     bins = torch.empty(scores2d.shape, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         C.check(L.gvcnn_bins_from_scores(_ptr(scores2d), _ptr(bins), None, _ptr(status), scores2d.numel(),
                                          num_group, int(multiplier or 0), 0, int(clamp or deferred is not None),
                                          _stream()), "gvcnn_bins_from_scores")
@@ -456,7 +505,7 @@ def group_scheme(view_discrimination_score, num_group, num_views, multiplier=Non
     bins = _bins_from_scores(s2, num_group, check=check, multiplier=multiplier)
     rows = bins.shape[0]
     scheme = torch.empty((rows, num_group, num_views), dtype=torch.int32, device=bins.device)
-    with torch.cuda.device(bins.device):
+    with _on(bins.device):
         C.check(C.lib().gvcnn_bins_to_scheme(_ptr(bins), _ptr(scheme), rows, num_views, num_group, _stream()),
                 "gvcnn_bins_to_scheme")
     out = scheme[0] if rows == 1 else scheme
@@ -487,7 +536,7 @@ def _scheme_to_bins(g_schemes: torch.Tensor, check=True):
     rows, G, V = sc.shape
     status = _new_status(sc.device) if check else None
     bins = torch.empty((rows, V), dtype=torch.int32, device=sc.device)
-    with torch.cuda.device(sc.device):
+    with _on(sc.device):
         C.check(C.lib().gvcnn_scheme_to_bins(_ptr(sc), _ptr(bins), _ptr(status), rows, V, G, _stream()),
                 "gvcnn_scheme_to_bins")
     if check:
@@ -507,7 +556,7 @@ def group_weight(g_schemes):
     bins, G = _scheme_to_bins(g_schemes)
     rows, V = bins.shape
     w = torch.empty((rows, G), dtype=torch.float32, device=bins.device)
-    with torch.cuda.device(bins.device):
+    with _on(bins.device):
         C.check(C.lib().gvcnn_group_weight(_ptr(bins), _ptr(w), rows, V, G, _stream()), "gvcnn_group_weight")
     out = w[0] if g_schemes.dim() == 2 else w
     return _tag(out, kind="weight", bins=bins)
@@ -544,7 +593,7 @@ def _pool_fuse_fwd(fv: _Views, bins: torch.Tensor, G: int, pool: str, empty_fill
         mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
     P = torch.empty((G, fv.B, fv.D), dtype=fv.dtype, device=dev) if want_groups else None
     status = _new_status(dev) if want_status else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         C.check(C.lib().gvcnn_pool_fuse_fwd(fv.arg, _ptr(bins), bin_stride, w_ptr, w_stride, _ptr(S), _ptr(P),
                                             _ptr(mask), _ptr(status), fv.B, fv.V, fv.D, G, _pool_code(pool, variant),
                                             ctypes.c_float(empty_fill), fv.layout, dt, _stream()),
@@ -555,7 +604,7 @@ def _pool_fuse_fwd(fv: _Views, bins: torch.Tensor, G: int, pool: str, empty_fill
 def _pool_fuse_bwd(dS: torch.Tensor, fv_like: _Views, bins, bin_stride, weights, w_stride, mask, G, pool, variant=0):
     dS = dS.contiguous()
     out, gv = fv_like.empty_like()
-    with torch.cuda.device(dS.device):
+    with _on(dS.device):
         C.check(C.lib().gvcnn_pool_fuse_bwd(_ptr(dS), _ptr(bins), bin_stride, _ptr(weights), w_stride,
                                             _ptr(mask), gv.arg, None, gv.B, gv.V, gv.D, G,
                                             _pool_code(pool, variant), gv.layout, _dtype_code(gv.dtype), _stream()),
@@ -653,7 +702,7 @@ class _PoolFuseGapFn(torch.autograd.Function):
         status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dev)
         ws_bytes = L.gvcnn_pool_fuse_gap_workspace_bytes(fv.B, Cch, HW, dt)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             C.check(L.gvcnn_pool_fuse_gap_fwd(fv.arg, _ptr(bins_c), bstride, _ptr(out), _ptr(mask), _ptr(status),
                                               _ptr(ws), ws_bytes, fv.B, fv.V, HW, Cch, G, _POOL[pool],
                                               ctypes.c_float(empty_fill), fv.layout, dt, _stream()),
@@ -671,7 +720,7 @@ class _PoolFuseGapFn(torch.autograd.Function):
         dOut = dOut.contiguous()
         out, gv = fv.empty_like()
         status = torch.zeros(C.STATUS_WORDS, dtype=torch.int32, device=dOut.device)
-        with torch.cuda.device(dOut.device):
+        with _on(dOut.device):
             C.check(C.lib().gvcnn_pool_fuse_gap_bwd(_ptr(dOut), _ptr(bins_c), ctx.bstride, _ptr(mask), gv.arg,
                                                     _ptr(status), gv.B, gv.V, ctx.HW, ctx.Cch, ctx.G, _POOL[ctx.pool],
                                                     gv.layout, _dtype_code(gv.dtype), _stream()),
@@ -885,7 +934,7 @@ def _fused_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, want_mask, s
     mask = None
     if want_mask and pool == "max":
         mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         C.check(L.gvcnn_grouping_fusion_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(x), _ptr(scores), _ptr(bins),
                                             _ptr(flags), _ptr(S), _ptr(mask), _ptr(status), fv.B, fv.V, rv.D, fv.D,
                                             G, _pool_code(pool, variant), ctypes.c_float(empty_fill), rv.layout,
@@ -1051,7 +1100,7 @@ def _batch_fwd(W, b, G, pool, empty_fill, rv, fv, edge_ulps, clamp, want_mask, s
     if want_mask and pool == "max":
         mask = torch.empty(((fv.V + 7) // 8, fv.B, fv.D), dtype=torch.uint8, device=dev)
     fn, user = exchange_c if exchange_c is not None else (None, None)
-    with torch.cuda.device(dev):
+    with _on(dev):
         C.check(L.gvcnn_grouping_fusion_batch_fwd(rv.arg, _ptr(Wc), _ptr(bc), fv.arg, _ptr(xb), _ptr(xsum), _ptr(xm),
                                                   _ptr(scores), _ptr(bins), _ptr(flags), _ptr(S), _ptr(mask),
                                                   _ptr(status), fv.B, fv.V, rv.D, fv.D, G, int(multiplier or 0),
@@ -1132,7 +1181,7 @@ class _PaperModeFn(torch.autograd.Function):
                        status=status)
         dev = fv.device
         weights = torch.empty((rv.B, G), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             C.check(L.gvcnn_group_weight_from_scores(_ptr(sr.scores), _ptr(sr.bins), _ptr(weights), rv.B, rv.V, G,
                                                      _stream()), "gvcnn_group_weight_from_scores")
         S, mask, _, _, bins_c, bstride, w_c, wstride = _pool_fuse_fwd(fv, sr.bins, G, pool, 0.0, weights,
@@ -1165,7 +1214,7 @@ class _PaperModeFn(torch.autograd.Function):
         dbias = scratch[n_dw + n_dx + n_W:n_dw + n_dx + n_W + rv.V]
         ws = scratch[n_dw + n_dx + n_W + rv.V:]
         dR_out, dR_views = (rv.empty_like() if ctx.need_dr else (None, None))
-        with torch.cuda.device(dev):
+        with _on(dev):
             C.check(L.gvcnn_pool_fuse_bwd_weights(fv.arg, _ptr(dS2), _ptr(S), _ptr(bins_c), ctx.bstride, _ptr(w_c),
                                                   ctx.wstride, _ptr(dweights), fv.B, fv.V, fv.D, G, _POOL[pool],
                                                   fv.layout, _dtype_code(fv.dtype), _stream()),

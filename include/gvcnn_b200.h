@@ -147,6 +147,20 @@ int gvcnn_score_bin(const float *x, float denom, float *x_mean, float *scores, i
                     int32_t *flags, int32_t *status, int64_t n, int G, int multiplier,
                     int edge_ulps, int clamp, const float *xabs, int bound_terms, void *stream);
 
+/* gvcnn_batch_sum_x + [exchange] + gvcnn_score_bin(denom = global_count) for the
+ * literal batch mode (nets/model.py:146-147, :23) - ONE launch, with the cross-rank
+ * all-reduce of the V sums issued from inside the kernel, when `exchange` is null
+ * or gvcnn_comm_allreduce_f32 (any other callback: three launches around it).
+ * x [B, V] (gvcnn_view_score_fwd's output); xsum [V] (the global sums on return);
+ * x_mean / scores / flags (nullable), bins: ONE [V] row.  global_count, exchange:
+ * as in gvcnn_grouping_fusion_batch_fwd, which is gvcnn_view_score_fwd + this +
+ * gvcnn_pool_fuse_fwd. */
+typedef int (*gvcnn_exchange_fn)(void *user, float *xsum_dev, int n, void *stream);
+int gvcnn_batch_mean_bin(const float *x, float *xsum, float *x_mean, float *scores, int32_t *bins,
+                         int32_t *flags, int32_t *status, int B, int V, int G, int multiplier,
+                         int edge_ulps, int clamp, int64_t global_count,
+                         gvcnn_exchange_fn exchange, void *exchange_user, void *stream);
+
 /* gvcnn_view_score_fwd + gvcnn_score_bin(denom = 1) in ONE kernel: the
  * per-shape path (SURVEY.md D5 'shape').  Replaces the device->host->device
  * hop of train.py:270-288.  x (nullable), scores, bins: [B, V]. */
@@ -255,7 +269,6 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
  * global_count: the number of shapes the mean is over (B, or the sum over the
  * ranks of a sharded batch).  exchange (nullable) as in gvcnn_grouping_fusion_host.
  * All launches are chained with programmatic dependent launch. */
-typedef int (*gvcnn_exchange_fn)(void *user, float *xsum_dev, int n, void *stream);
 int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *bias, const void *F,
                                     float *x, float *xsum, float *x_mean, float *scores, int32_t *bins,
                                     int32_t *flags, void *S, uint8_t *tie_mask, int32_t *status,

@@ -1401,3 +1401,22 @@ def test_p2p_comm_single_rank(model):
         assert torch.equal(S1, S2) and torch.equal(sr1.bins, sr2.bins)
     finally:
         assert L.gvcnn_comm_destroy(comm) == 0
+
+
+def test_group_scheme_deferred_check(model):
+    """check='deferred': the reference's IndexError / ValueError (nets/model.py:23) without a synchronisation inside
+    the step - the counters travel to pinned host memory asynchronously and the NEXT call, or check_deferred(),
+    raises; out-of-range bins are clamped meanwhile; a raise clears the counters."""
+    ok = model.group_scheme([[0.31, 0.52, 0.07]], 10, 3, check="deferred")
+    model.check_deferred()                                               # nothing to report
+    np.testing.assert_array_equal(ok.cpu().numpy(), O.group_scheme([[0.31, 0.52, 0.07]], 10, 3))
+    bad = model.group_scheme([[1.0, 0.3, 0.2]], 10, 3, check="deferred")  # score 1.0 -> bin 10 of 10: no raise yet
+    assert int(bad.sum()) == 3 and int(bad[9, 0]) == 1                    # clamped into the last group meanwhile
+    with pytest.raises(IndexError):
+        model.check_deferred()
+    model.check_deferred()                                               # reported once, then clean
+    model.group_scheme([[float("nan"), 0.3, 0.2]], 10, 3, check="deferred")
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError):                                      # the next call polls the finished copy
+        model.group_scheme([[0.1, 0.3, 0.2]], 10, 3, check="deferred")
+    model.check_deferred()
