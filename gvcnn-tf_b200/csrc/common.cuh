@@ -310,6 +310,43 @@ __device__ __forceinline__ void mean_of_sum(float (&m)[E], const int n)
     }
 }
 
+// The same mean, with the division of the other counts done by div_by_rcp's multiply + two FMAs behind one range test
+// for all E elements (bit tests on the magnitudes: zero passes - the sequence returns 0 for it and the sign is put
+// back below - anything else outside 2^-100 <= |a| < 2^100 sends the whole vector through the IEEE sequence).
+template <int E>
+__device__ __forceinline__ void mean_of_sum_rcp(float (&m)[E], const int n)
+{
+    if (n <= 1) return;
+    if ((n & (n - 1)) == 0) {
+        const float r = __uint_as_float((uint32_t)(127 - (31 - __clz(n))) << 23);  // 2^-log2(n)
+#pragma unroll
+        for (int e = 0; e < E; ++e) m[e] = __fmul_rn(m[e], r);
+        return;
+    }
+    const float fn = (float)n;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t u = __float_as_uint(m[e]) & 0x7fffffffu;
+        lo = min(lo, u - 1u);  // zero wraps to the top and drops out of the minimum
+        hi = max(hi, u);
+    }
+    if (lo >= (27u << 23) - 1u && hi < (227u << 23)) {
+        const float r = __frcp_rn(fn);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float q = __fmul_rn(m[e], r);
+            const float rem = __fmaf_rn(-fn, q, m[e]);
+            const float res = __fmaf_rn(rem, r, q);
+            // the quotient has the sign of the dividend; the FMA chain loses it only for -0 (res = +0)
+            m[e] = __uint_as_float((__float_as_uint(res) & 0x7fffffffu) | (__float_as_uint(m[e]) & 0x80000000u));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) m[e] = __fdiv_rn(m[e], fn);
+    }
+}
+
 // ---- packed float32 pairs (Blackwell: add/mul/fma .f32x2 - two IEEE round-to-nearest results per instruction) ----
 // The instruction-bound variants of the pooling kernels (bf16 data: half the bytes per element, the same float32
 // arithmetic per element) spend most of their issue slots on the accumulator updates acc += fill and
@@ -370,11 +407,39 @@ template <> struct Elem<float> {
         return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
                           __float_as_uint(f[3]));
     }
+    __device__ static __forceinline__ void add_to(float (&a)[4], const uint4 &r)  // a[e] = RN(a[e] + r_e)
+    {
+        float x[4];
+        unpack(r, x);
+        vec_add(a, x);
+    }
     __device__ static __forceinline__ float to_float(float v) { return v; }
     __device__ static __forceinline__ float from_float(float v) { return v; }
 };
+#ifndef GVCNN_BF16_MIXED_ADD
+#define GVCNN_BF16_MIXED_ADD 1  // A/B builds: 0 = widen (shift / mask) and add.f32x2
+#endif
 template <> struct Elem<__nv_bfloat16> {
     static constexpr int kVec = 8;
+    // a[e] = RN(a[e] + float(r_e)).  sm_100 has a mixed-precision add (add.rn.f32.bf16 -> FHADD.BF16 with a half-select
+    // on the bf16 operand): the widening is exact and part of the instruction, so the result is the one of
+    // unpack + add.f32 - two instructions per element pair instead of three (shift, mask, packed add).
+    __device__ static __forceinline__ void add_to(float (&a)[8], const uint4 &r)
+    {
+#if GVCNN_BF16_MIXED_ADD
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\t"
+                "add.rn.f32.bf16 %1, hi, %1;\n\t}"
+                : "+f"(a[2 * i]), "+f"(a[2 * i + 1])
+                : "r"(w[i]));
+#else
+        float x[8];
+        unpack(r, x);
+        vec_add(a, x);
+#endif
+    }
     __device__ static __forceinline__ void unpack(const uint4 &r, float (&f)[8])
     {
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -389,9 +454,8 @@ template <> struct Elem<__nv_bfloat16> {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i]));
-            const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i + 1]));
-            w[i] = lo | (hi << 16);
+            const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);  // one cvt.rn.bf16x2.f32
+            w[i] = *reinterpret_cast<const uint32_t *>(&p);
         }
         return make_uint4(w[0], w[1], w[2], w[3]);
     }

@@ -49,9 +49,9 @@ gap_score_kernel(const ViewPtrs mp, const int64_t m_sb, const float *__restrict_
     pdl_launch_dependents();
     const T *__restrict__ src = reinterpret_cast<const T *>(mp.p[v]) + (int64_t)b * m_sb + (int64_t)p0 * C + lane * E;
 
-    float acc[NA];
+    float acc[NB][E];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < NA; ++i) acc[i / E][i % E] = 0.0f;
     uint4 buf[2][NB];
     if (np > 0) {
 #pragma unroll
@@ -64,10 +64,7 @@ gap_score_kernel(const ViewPtrs mp, const int64_t m_sb, const float *__restrict_
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
-            float f[E];
-            Elem<T>::unpack(buf[0][u], f);
-#pragma unroll
-            for (int e = 0; e < E; ++e) acc[u * E + e] = __fadd_rn(acc[u * E + e], f[e]);
+            Elem<T>::add_to(acc[u], buf[0][u]);
         }
         if (j + 1 < np) {
             if (j + 2 < np) {
@@ -76,10 +73,7 @@ gap_score_kernel(const ViewPtrs mp, const int64_t m_sb, const float *__restrict_
             }
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
-                float f[E];
-                Elem<T>::unpack(buf[1][u], f);
-#pragma unroll
-                for (int e = 0; e < E; ++e) acc[u * E + e] = __fadd_rn(acc[u * E + e], f[e]);
+                Elem<T>::add_to(acc[u], buf[1][u]);
             }
         }
     }
@@ -89,7 +83,7 @@ gap_score_kernel(const ViewPtrs mp, const int64_t m_sb, const float *__restrict_
 #pragma unroll
         for (int e = 0; e < E; e += 4)
             *reinterpret_cast<float4 *>(&part[warp][(u * 32 + lane) * E + e]) =
-                make_float4(acc[u * E + e], acc[u * E + e + 1], acc[u * E + e + 2], acc[u * E + e + 3]);
+                make_float4(acc[u][e], acc[u][e + 1], acc[u][e + 2], acc[u][e + 3]);
     __syncthreads();
     if (warp != 0) return;
 

@@ -22,6 +22,15 @@ struct __align__(16) BwdPlan {
     uint32_t first_mask;            // bit k: sorted view k starts a group
 };
 
+// prmt.b32, generic mode: a selector nibble with bit 3 set replicates the top bit of the selected byte over the
+// result byte (PTX ISA, prmt) - 0x00 or 0xff per byte
+__device__ __forceinline__ uint32_t prmt_sign(const uint32_t a, const uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+
 // GAP: dS is the gradient of the global average pool that follows the fusion, [B, C] (D = HW * C,
 // channel-last): dS[b, p, c] = dOut[b, c] / HW (tf.reduce_mean's gradient), never materialised.
 template <typename T, int POOL, int V, int NT, bool GAP, bool WTS>
@@ -145,25 +154,33 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
         for (int k = 0; k < V; ++k) {
             if (k == 0 || ((fm >> k) & 1u)) {  // uniform: a group starts here
                 const uint32_t seg = plan.seg[k];
-                const float w = wts ? plan.gw[k] : (float)(1 + __popc(seg));
+                const int n = __popc(seg);
+                const float w = wts ? plan.gw[k] : (float)(1 + n);
                 float val[E];
+                if (n == 1) {  // uniform: a group of one view - num_selected is 1 wherever the value is kept
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const uint32_t half = (e & 1) ? 0xffff0000u : 0x0000ffffu;
-                    const uint32_t lo = (seg & 0xffffu) * 0x00010001u, hi = (seg >> 16) * 0x00010001u;
-                    const int nsel = __popc(me2[e >> 1] & lo & half) + (V > 16 ? __popc(me2b[e >> 1] & hi & half) : 0);
-                    val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));
+                    for (int e = 0; e < E; ++e) val[e] = __fmul_rn(t[e], w);  // (1 / 1) * g1 = g1 exactly
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const uint32_t half = (e & 1) ? 0xffff0000u : 0x0000ffffu;
+                        const uint32_t lo = (seg & 0xffffu) * 0x00010001u, hi = (seg >> 16) * 0x00010001u;
+                        const int nsel = __popc(me2[e >> 1] & lo & half) + (V > 16 ? __popc(me2b[e >> 1] & hi & half) : 0);
+                        val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));
+                    }
                 }
                 const uint4 pk = Elem<T>::pack(val);
                 val2[0] = pk.x; val2[1] = pk.y; val2[2] = pk.z; val2[3] = pk.w;
             }
+            // view k keeps the value where its tie bit is set: bit (k & 7) of element e's byte in plane k >> 3.  Shifted
+            // to the byte's top bit, one PRMT in sign-replicate mode turns the two bytes of an element pair into the
+            // 0xffff / 0x0000 halves that mask the packed pair (shift per word + PRMT + AND per pair).
             uint4 o;
             uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+            const uint32_t sh0 = pwd[k >> 3][0] << (7 - (k & 7)), sh1 = pwd[k >> 3][NW - 1] << (7 - (k & 7));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t bits = ((k < 16 ? me2[i] : me2b[i]) >> (k & 15)) & 0x00010001u;
-                ow[i] = val2[i] & (bits * 0xffffu);
-            }
+            for (int i = 0; i < 4; ++i)
+                ow[i] = val2[i] & prmt_sign((i >> 1) ? sh1 : sh0, (i & 1) ? 0xBBAAu : 0x9988u);
             stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, o);
         }
     } else {
@@ -292,9 +309,12 @@ int launch_pool_fuse_gap_bwd(const void *dOut, const int32_t *bins, int64_t bin_
     if (C % td != 0) return -1000;
 #define GVCNN_GAPB_CASE(T_)                                                                                   \
     switch (V) {                                                                                              \
+    case 4: return launch_bwd_fast_v<T_, 4>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
     case 6: return launch_bwd_fast_v<T_, 6>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
     case 8: return launch_bwd_fast_v<T_, 8>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW);   \
     case 12: return launch_bwd_fast_v<T_, 12>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW); \
+    case 16: return launch_bwd_fast_v<T_, 16>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW); \
+    case 20: return launch_bwd_fast_v<T_, 20>(dOut, bins, bin_sb, mask, nullptr, 0, gp, g_sb, status, B, D, G, pool, st, C, HW); \
     default: return -1000;                                                                                    \
     }
     if (dtype == GVCNN_F32) { GVCNN_GAPB_CASE(float) }

@@ -99,7 +99,7 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
 
     float acc[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+    for (int e = 0; e < E; ++e) acc[e] = -0.0f;  // add_n starts from its first term: -0 + t == t for every t
     uint32_t pw[(E + 3) / 4];
 #pragma unroll
     for (int i = 0; i < (E + 3) / 4; ++i) pw[i] = 0u;
@@ -109,12 +109,11 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
     while (k < V) {
         const int g = plan.gbin[k];
         const int len = plan.glen[k];
-        if (fill != 0.0f)
-            for (int q = prev_g + 1; q < g; ++q) {  // empty groups: w = 1 (or given), P = fill
-                const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+        for (int q = prev_g + 1; q < g; ++q) {  // empty groups: w = 1 (or given), P = fill (a +-0 term when fill == 0)
+            const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
 #pragma unroll
-                for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
-            }
+            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+        }
         if (Pout)
             for (int q = prev_g + 1; q < g; ++q) store_fill<T, VEC>(Pout + ((int64_t)q * B) * D + out_off, fill);
         float m[E];
@@ -167,12 +166,11 @@ __global__ void pool_fuse_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, cons
         prev_g = g;
         k += len;
     }
-    if (fill != 0.0f)
-        for (int q = prev_g + 1; q < G; ++q) {
-            const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+    for (int q = prev_g + 1; q < G; ++q) {
+        const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
 #pragma unroll
-            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
-        }
+        for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
+    }
     if (Pout)
         for (int q = prev_g + 1; q < G; ++q) store_fill<T, VEC>(Pout + ((int64_t)q * B) * D + out_off, fill);
     const float sumw = plan.sumw;  // G + V for the reference's weights (exact in any order)
@@ -243,7 +241,7 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
 
     float acc[E], m[E], m_in[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = m[e] = m_in[e] = 0.0f;
+    for (int e = 0; e < E; ++e) { acc[e] = -0.0f; m[e] = m_in[e] = 0.0f; }  // add_n starts from its first term
     const int64_t out_off = (int64_t)b * D + d0 + e0;
     int prev_g = -1, cur_g = -1, len = 0, gs = 0;  // gs = sorted position where the open group started
     float w = 0.0f;
@@ -306,11 +304,9 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
     };
     auto skip_empty = [&](int from, int to) {  // empty groups from..to-1: w = 1 (or given), P = fill
         for (int q = from; q < to; ++q) {
-            if (fill != 0.0f) {
-                const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;
+            const float term = wrow ? __fmul_rn(__ldg(wrow + q), fill) : fill;  // a +-0 term when fill == 0
 #pragma unroll
-                for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
-            }
+            for (int e = 0; e < E; ++e) acc[e] = __fadd_rn(acc[e], term);
             if (Pout && active) store_fill<T, true>(Pout + ((int64_t)q * B) * D + out_off, fill);
         }
     };
@@ -327,8 +323,7 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
         }
         for (int j = 0; j < nv; ++j) {
             const int k = k0 + j;
-            float x[E];
-            Elem<T>::unpack(*reinterpret_cast<const uint4 *>(col + (size_t)j * kRowStride), x);
+            const uint4 rv = *reinterpret_cast<const uint4 *>(col + (size_t)j * kRowStride);
             const int g = plan.gbin[k];
             if (g != cur_g) {  // uniform: view k starts a group
                 if (cur_g >= 0) {
@@ -343,12 +338,14 @@ pool_fuse_fwd_chunked_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_
                 gs = k;
                 len = plan.glen[k];
                 w = plan.gw[k];
+                Elem<T>::unpack(rv, m);
+            } else if constexpr (POOL == GVCNN_POOL_MAX) {
+                float x[E];
+                Elem<T>::unpack(rv, x);
 #pragma unroll
-                for (int e = 0; e < E; ++e) m[e] = x[e];
+                for (int e = 0; e < E; ++e) m[e] = fmaxf(m[e], x[e]);
             } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    m[e] = (POOL == GVCNN_POOL_MAX) ? fmaxf(m[e], x[e]) : __fadd_rn(m[e], x[e]);
+                Elem<T>::add_to(m, rv);
             }
         }
         if constexpr (MASK) {  // the group still open at the end of the chunk: provisional bits for its members here

@@ -233,9 +233,12 @@ int launch_pool_fuse_gap_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bi
     if (G > 255) return -1000;
 #define GVCNN_GAP_CASE(T_)                                                                                    \
     switch (V) {                                                                                              \
+    case 4: return launch_gap_v<T_, 4, 2>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
     case 6: return launch_gap_v<T_, 6, 2>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
     case 8: return launch_gap_v<T_, 8, 2>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
     case 12: return launch_gap_v<T_, 12, 2>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
+    case 16: return launch_gap_v<T_, 16, 1>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
+    case 20: return launch_gap_v<T_, 20, 1>(fp, f_sb, bins, bin_sb, out, mask, status, partial, B, HW, C, G, pool, fill, st); \
     default: return -1000;                                                                                    \
     }
     if (dtype == GVCNN_F32) { GVCNN_GAP_CASE(float) }

@@ -61,10 +61,11 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #ifndef GVCNN_MEAN_CHUNKED
 #define GVCNN_MEAN_CHUNKED 1  // A/B builds: 0 = fully unrolled mean walk for every V (round 1)
 #endif
+#ifndef GVCNN_MEAN_CHUNKED_MINV
+#define GVCNN_MEAN_CHUNKED_MINV 4
+#endif
     // bf16 only: float32 mean at V = 20 is HBM-bound either way and measured 4 % slower chunked (135.8 vs 129.9 us)
-    constexpr bool kChunkedMean = GVCNN_MEAN_CHUNKED && (POOL == GVCNN_POOL_MEAN) && (V % 4 == 0) && V >= 12 && E == 8;
-#pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+    constexpr bool kChunkedMean = GVCNN_MEAN_CHUNKED && (POOL == GVCNN_POOL_MEAN) && (V % 4 == 0) && V >= GVCNN_MEAN_CHUNKED_MINV && E == 8;
     // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
     // in uniform registers and the per-view branches below are uniform branches
     const uint32_t fm = __reduce_or_sync(0xffffffffu, plan_s.first_mask);
@@ -73,6 +74,24 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #pragma unroll
     for (int i = 0; i < (V + 3) / 4; ++i)
         skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plan_s.skip)[i]);
+    // tf.add_n starts from its first term, so the accumulator starts from -0.0f, the identity of IEEE addition
+    // (-0 + t == t for every t, signed zeros included).  Empty groups still contribute their term w_g * fill; with
+    // fill == 0 and the reference's positive weights each of them is +0 and the walks below skip them.  The one place
+    // where such a term is visible is a sum that is otherwise -0 (every pooled value -0): -0 + +0 = +0 - which is
+    // the same as starting from +0.0f when there is at least one empty group, and changes nothing else.  The mean
+    // kernels (fill == 0 is their normal case) test exactly that.  The max kernels are at their register limit - any
+    // run-time choice here costs them spills (bf16 V = 12 with tie planes: 42.8 -> 47.6 us) - and always start from
+    // -0.0f: exact for every fill != 0 (the reference's is one); with max pooling AND fill == 0 AND an empty group,
+    // an element at which every view holds -0 comes out as -0 where the reference's sum gives +0.
+    float acc0 = -0.0f;
+    if constexpr (POOL == GVCNN_POOL_MEAN) {
+        uint32_t any_empty = tail_skip;
+#pragma unroll
+        for (int i = 0; i < (V + 3) / 4; ++i) any_empty |= skw[i];
+        if (!wts && fill == 0.0f && any_empty != 0u) acc0 = 0.0f;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = acc0;
     if (active && kPackedMax) {
         // bf16 max pooling: the max of bf16 values is exact in bf16, so the running group max stays
         // packed (2 elements per register, max.bf16x2) and is widened to float32 only when a group
@@ -108,7 +127,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);
                     acc_add_scaled(acc, w, m);
                 }
-                if (fill != 0.0f) {
+                if (fill != 0.0f || wts) {
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
@@ -159,27 +178,33 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
             }
         }
     } else if (active && kChunkedMean) {
-        // Mean pooling with many views: the sorted rows are walked four at a time - an outer loop that is NOT
-        // unrolled around a body that is - with the next four rows' loads in flight.  The fully unrolled walk below
-        // replicates the group-close code (mean_of_sum's three cases + the weighted add + the fill loop) V + 1 times:
-        // 113 KB of SASS at V = 20 bf16, and ncu shows the consumers starving on instruction fetch (stall
-        // no_instruction 2.6 per issue, instruction-cache hit rate 65 %, profiles/r02r_ncu_bf16_v20_mean.md).  Here it
-        // exists five times.  Same operations in the same order as the unrolled walk.  bf16 V = 20, D = 2048: 125.1 ->
-        // 96.9 us; D = 1024: 55.6 -> 43.5 us; V = 12: 27.5 -> 25.6 us (profiles/r02s_mean_chunked_ab.jsonl).
+        // bf16 mean pooling is bound by instruction issue and latency (two CTAs of four consumer warps per SM), not by
+        // HBM, so this walk is built for a short instruction stream:
+        //  * the sorted rows are walked CH at a time - an outer loop that is NOT unrolled around a body that is; the
+        //    fully unrolled walk below replicates the group-close code V + 1 times (113 KB of SASS at V = 20, consumers
+        //    starving on instruction fetch, profiles/r02r_ncu_bf16_v20_mean.md);
+        //  * a group's running sum starts from -0.0f, the identity of IEEE addition (-0 + x == x for every x, signed
+        //    zeros included), so every row takes the same eight mixed-precision adds and "first member of a group" is
+        //    no longer a second code path per row;
+        //  * the group mean uses the exact division by a precomputed reciprocal (div_by_rcp) behind ONE range test
+        //    for the eight elements instead of eight IEEE division sequences with their slow-path branches.
+        // Same operations on the same values in the same order as the unrolled walk.
         if constexpr (kChunkedMean) {
         constexpr int CH = 4;
         float m[E];
-        int cnt = 0, gcur = 0;
-        uint4 nxt[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) nxt[j] = *reinterpret_cast<const uint4 *>(col + j * kRowStride);
+        for (int e = 0; e < E; ++e) m[e] = -0.0f;
+        int cnt = 0, gcur = 0;
         auto close_group = [&](const int k) {  // acc += w_g * mean of the group that ended before sorted position k
             const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);
-            mean_of_sum(m, cnt);
+            mean_of_sum_rcp(m, cnt);
             acc_add_scaled(acc, w, m);
+#pragma unroll
+            for (int e = 0; e < E; ++e) m[e] = -0.0f;
+            cnt = 0;
         };
         auto fill_empty = [&](const uint32_t nskip) {
-            if (fill != 0.0f) {
+            if (fill != 0.0f || wts) {
 #pragma unroll 1
                 for (uint32_t q = 0; q < nskip; ++q) {
                     const float term = wts ? __fmul_rn(wall[gcur + q], fill) : fill;
@@ -192,27 +217,18 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
         for (int k0 = 0; k0 < V; k0 += CH) {
             uint4 cur[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
-            if (k0 + CH < V) {
-#pragma unroll
-                for (int j = 0; j < CH; ++j) nxt[j] = *reinterpret_cast<const uint4 *>(col + (k0 + CH + j) * kRowStride);
-            }
-            const uint32_t fmc = fm >> k0;                                                       // uniform
-            const uint32_t skc = reinterpret_cast<const uint32_t *>(plan_s.skip)[k0 >> 2];       // uniform (broadcast)
+            for (int j = 0; j < CH; ++j) cur[j] = *reinterpret_cast<const uint4 *>(col + (k0 + j) * kRowStride);
+            const uint32_t fmc = fm >> k0;                                                                  // uniform
+            const uint32_t skc = reinterpret_cast<const uint32_t *>(plan_s.skip)[k0 >> 2] >> (8 * (k0 & 3));  // uniform
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-                if ((k0 + j == 0) || ((fmc >> j) & 1u)) {  // uniform: a group ends / starts here
-                    if (k0 + j > 0) close_group(k0 + j);
+                if ((fmc >> j) & 1u) {  // uniform: a group starts here (bit 0 of the mask is always set)
+                    if (cnt > 0) close_group(k0 + j);
                     fill_empty((skc >> (8 * j)) & 0xffu);
-                    Elem<T>::unpack(cur[j], m);
-                    cnt = 1;
                     ++gcur;
-                } else {
-                    float x[E];
-                    Elem<T>::unpack(cur[j], x);
-                    vec_add(m, x);
-                    ++cnt;
                 }
+                Elem<T>::add_to(m, cur[j]);
+                ++cnt;
             }
         }
         close_group(V);
@@ -249,7 +265,7 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, cnt);
                     acc_add_scaled(acc, w, m);
                 }
-                if (fill != 0.0f) {  // empty groups in between / after: w = 1 (or given), P = fill
+                if (fill != 0.0f || wts) {  // empty groups in between / after: w = 1 (or given), P = fill
                     const uint32_t nskip = (k == V) ? tail_skip : ((skw[(k < V ? k : 0) >> 2] >> (8 * (k & 3))) & 0xffu);
 #pragma unroll 1
                     for (uint32_t q = 0; q < nskip; ++q) {
@@ -264,13 +280,13 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                     ++gcur;
                 }
             } else {
-                float x[E];
-                Elem<T>::unpack(raw[k < V ? k : 0], x);
                 if constexpr (POOL == GVCNN_POOL_MAX) {
+                    float x[E];
+                    Elem<T>::unpack(raw[k < V ? k : 0], x);
 #pragma unroll
                     for (int e = 0; e < E; ++e) m[e] = fmaxf(m[e], x[e]);
                 } else {
-                    vec_add(m, x);
+                    Elem<T>::add_to(m, raw[k < V ? k : 0]);
                 }
                 ++cnt;
             }

@@ -285,7 +285,7 @@ int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *
  * the forward and the read of dS in the backward).  Per-position arithmetic is
  * exactly gvcnn_pool_fuse_fwd's; positions are added in order (split into a few
  * ascending chunks for parallelism, see gvcnn_pool_fuse_gap_workspace_bytes),
- * then divided by HW.  Supported: 16-byte aligned rows, V in {6, 8, 12},
+ * then divided by HW.  Supported: 16-byte aligned rows, V in {4, 6, 8, 12, 16, 20},
  * C a multiple of 1024 (f32) / 2048 (bf16), G <= 255, the reference's own
  * weights; anything else returns GVCNN_E_UNSUPPORTED (use gvcnn_pool_fuse_fwd
  * and pool afterwards).  tie_mask as in gvcnn_pool_fuse_fwd ([ceil(V/8), B, D]).

@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gvcnn_tf_b200 import _cabi as C  # noqa: E402
 ap = argparse.ArgumentParser(); ap.add_argument("--N", type=int, default=128); ap.add_argument("--V", type=int, default=6)
 ap.add_argument("--bf16", action="store_true"); args = ap.parse_args()
+if os.environ.get("GVCNN_LIB"):
+    C.SO_PATH = os.environ["GVCNN_LIB"]
 L = C.lib(); dev = torch.device("cuda:0"); N, V, HW, Cr, G = args.N, args.V, 100, 1024, 10
 td, dt, es = (torch.bfloat16, C.BF16, 2) if args.bf16 else (torch.float32, C.F32, 4)
 p = lambda t: ctypes.c_void_p(t.data_ptr()); sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1061,12 +1061,18 @@ def test_sweep_grid_parity(model, c_oracle, V, G, D, pool, fill, dtype):
     np.testing.assert_array_equal(x.grad.float().cpu().numpy(), wantg)
 
 
-@pytest.mark.parametrize("V,D", [(12, 2048), (16, 1024), (5, 100), (40, 1024)])
-def test_mean_division_shortcuts_are_exact(model, V, D):
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,D", [(12, 2048), (16, 1024), (5, 100), (40, 1024), (6, 1024), (20, 2048)])
+def test_mean_division_shortcuts_are_exact(model, V, D, dtype):
     """mean_of_sum (csrc/common.cuh) skips the division for singleton groups and multiplies by 2^-k for
     power-of-two group sizes; both must equal the float32 division for every value class: subnormal sums and
     quotients, the largest finite values, infinities produced by the sum, signed zeros.  Group sizes 1..V all
-    occur (shape i puts its first i+1 views in one group); ring, generic and chunked kernels."""
+    occur (shape i puts its first i+1 views in one group); ring, generic and chunked kernels.  bf16: the ring's mean
+    walk starts every group sum from -0.0f and adds the bf16 rows with the mixed-precision add (add.rn.f32.bf16), and
+    divides by a precomputed reciprocal behind a range test - bf16 subnormals, signed zeros, sums that overflow and
+    values outside the reciprocal's range must all come out as the float32 division of the float32 sum, rounded."""
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "fp32" else O.round_bf16
     G = V
     B = 2 * V
     rng = np.random.default_rng(V)
@@ -1074,23 +1080,25 @@ def test_mean_division_shortcuts_are_exact(model, V, D):
     F = (rng.choice(mag, (B, V, D)) * rng.choice(np.array([-1, 1], np.float32), (B, V, D))).astype(np.float32)
     F[:, :, :8] = 0.0
     F[:, ::2, :4] = -0.0
+    F[:, :, 8:12] = -0.0                    # all-negative-zero columns: the group sum itself is -0
+    F = rnd(F)
     bins = np.zeros((B, V), dtype=np.int32)
     for i in range(B):
         n = i % V + 1                       # the first n views share group 0, the others get their own
         bins[i, n:] = np.arange(1, V - n + 1)
     with np.errstate(over="ignore", invalid="ignore"):
-        want = O.pool_fuse_fwd(F, bins, G, "mean", 0.0)
-    x = dev(F).requires_grad_(True)
+        want = rnd(O.pool_fuse_fwd(F, bins, G, "mean", 0.0))
+    x = dev(F, td).requires_grad_(True)
     S = model.pool_fuse(x, dev(bins), G, pool="mean", empty_fill=0.0)
-    got = S.detach().cpu().numpy()
+    got = S.detach().float().cpu().numpy()
     np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
     assert np.array_equal(np.isnan(got), np.isnan(want))
     # the same shortcuts in the backward (g / n): gradients of every magnitude class
-    dS = (rng.choice(mag, (B, D)) * rng.choice(np.array([-1, 1], np.float32), (B, D))).astype(np.float32)
-    S.backward(dev(dS))
+    dS = rnd((rng.choice(mag, (B, D)) * rng.choice(np.array([-1, 1], np.float32), (B, D))).astype(np.float32))
+    S.backward(dev(dS, td))
     with np.errstate(over="ignore", invalid="ignore"):
-        wantg = O.pool_fuse_bwd(dS, F, bins, G, "mean")
-    gotg = x.grad.cpu().numpy()
+        wantg = rnd(O.pool_fuse_bwd(dS, F, bins, G, "mean"))
+    gotg = x.grad.float().cpu().numpy()
     ok = ~np.isnan(wantg)
     np.testing.assert_array_equal(gotg.view(np.uint32)[ok], wantg.view(np.uint32)[ok])
     assert np.array_equal(np.isnan(gotg), np.isnan(wantg))
@@ -1213,7 +1221,8 @@ def test_one_call_forward_equals_staged_path(model, c_oracle, B, V, D, pool, dty
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0)])
-@pytest.mark.parametrize("N,V,h,w,Cc", [(4, 6, 10, 10, 2048), (37, 12, 3, 3, 2048), (300, 12, 1, 1, 2048), (2, 8, 5, 4, 4096)])
+@pytest.mark.parametrize("N,V,h,w,Cc", [(4, 6, 10, 10, 2048), (37, 12, 3, 3, 2048), (300, 12, 1, 1, 2048), (2, 8, 5, 4, 4096),
+                                        (5, 4, 3, 2, 2048), (3, 16, 2, 3, 2048), (3, 20, 3, 3, 2048)])
 def test_gap_folded_pooling(model, c_oracle, N, V, h, w, Cc, pool, fill, dtype):
     """pooling + fusion + GlobalAveragePooling2D (nets/model.py:154-163) without writing the fused
     map.  Forward = mean over positions of the oracle's S; backward = the oracle's dF for dS = dOut / (h*w).
