@@ -228,7 +228,13 @@ int gvcnn_group_weight(const int32_t *bins, float *weights, int rows, int V, int
  *    [ceil(V/8), B, D]; bit k%8 of plane k/8 <=> the k-th view in (bin, view)
  *    order attains its group's maximum.  Opaque to callers.
  * status (nullable): bins outside [0, G) are counted in
- *    status[GVCNN_STATUS_BIN_RANGE] and clamped for memory safety. */
+ *    status[GVCNN_STATUS_BIN_RANGE] and clamped for memory safety.
+ * Signed zeros: the sum starts from its first term like tf.add_n does and an
+ *    empty group's term w_g * empty_fill takes part in it, so S carries the
+ *    reference's sign of zero too.  One exception, on the V-specialised max
+ *    pooling kernels only: pool = MAX with empty_fill == 0 (not a reference
+ *    combination), at an element where every view holds -0 and some group is
+ *    empty, gives -0 where the reference's sum gives +0. */
 int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b,
                         const float *weights, int64_t weight_stride_b,
                         void *S, void *group_desc, uint8_t *tie_mask, int32_t *status,
