@@ -310,9 +310,39 @@ __device__ __forceinline__ void mean_of_sum(float (&m)[E], const int n)
     }
 }
 
-// The same mean, with the division of the other counts done by div_by_rcp's multiply + two FMAs behind one range test
-// for all E elements (bit tests on the magnitudes: zero passes - the sequence returns 0 for it and the sign is put
-// back below - anything else outside 2^-100 <= |a| < 2^100 sends the whole vector through the IEEE sequence).
+// The IEEE division sequence out of line: the fall-back of the vector division below, which would otherwise inline E
+// copies of it (with their slow-path branches) at every call site.
+static __device__ __noinline__ float fdiv_rn_outlined(const float a, const float b) { return __fdiv_rn(a, b); }
+
+// m[e] = RN(m[e] / fn) for a small positive integer fn with r = RN(1 / fn): div_by_rcp's multiply + two FMAs behind
+// ONE range test for all E elements (bit tests on the magnitudes: zero passes - the sequence returns 0 for it and the
+// sign is put back - anything else outside 2^-100 <= |a| < 2^100 sends the whole vector through the IEEE sequence).
+template <int E>
+__device__ __forceinline__ void div_vec_by_rcp(float (&m)[E], const float fn, const float r)
+{
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t u = __float_as_uint(m[e]) & 0x7fffffffu;
+        lo = min(lo, u - 1u);  // zero wraps to the top and drops out of the minimum
+        hi = max(hi, u);
+    }
+    if (lo >= (27u << 23) - 1u && hi < (227u << 23)) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float q = __fmul_rn(m[e], r);
+            const float rem = __fmaf_rn(-fn, q, m[e]);
+            const float res = __fmaf_rn(rem, r, q);
+            // the quotient has the sign of the dividend; the FMA chain loses it only for -0 (res = +0)
+            m[e] = __uint_as_float((__float_as_uint(res) & 0x7fffffffu) | (__float_as_uint(m[e]) & 0x80000000u));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) m[e] = fdiv_rn_outlined(m[e], fn);
+    }
+}
+
+// mean_of_sum with the division of the counts that are not powers of two done by div_vec_by_rcp.
 template <int E>
 __device__ __forceinline__ void mean_of_sum_rcp(float (&m)[E], const int n)
 {
@@ -324,27 +354,7 @@ __device__ __forceinline__ void mean_of_sum_rcp(float (&m)[E], const int n)
         return;
     }
     const float fn = (float)n;
-    uint32_t lo = 0xffffffffu, hi = 0u;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const uint32_t u = __float_as_uint(m[e]) & 0x7fffffffu;
-        lo = min(lo, u - 1u);  // zero wraps to the top and drops out of the minimum
-        hi = max(hi, u);
-    }
-    if (lo >= (27u << 23) - 1u && hi < (227u << 23)) {
-        const float r = __frcp_rn(fn);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const float q = __fmul_rn(m[e], r);
-            const float rem = __fmaf_rn(-fn, q, m[e]);
-            const float res = __fmaf_rn(rem, r, q);
-            // the quotient has the sign of the dividend; the FMA chain loses it only for -0 (res = +0)
-            m[e] = __uint_as_float((__float_as_uint(res) & 0x7fffffffu) | (__float_as_uint(m[e]) & 0x80000000u));
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) m[e] = __fdiv_rn(m[e], fn);
-    }
+    div_vec_by_rcp(m, fn, __frcp_rn(fn));
 }
 
 // ---- packed float32 pairs (Blackwell: add/mul/fma .f32x2 - two IEEE round-to-nearest results per instruction) ----

@@ -33,55 +33,69 @@ __device__ __forceinline__ uint32_t prmt_sign(const uint32_t a, const uint32_t s
 
 // GAP: dS is the gradient of the global average pool that follows the fusion, [B, C] (D = HW * C,
 // channel-last): dS[b, p, c] = dOut[b, c] / HW (tf.reduce_mean's gradient), never materialised.
-template <typename T, int POOL, int V, int NT, bool GAP, bool WTS>
+template <typename T, int POOL, int V, int NT, bool GAP, bool WTS, int UPC>
 __global__ void __launch_bounds__(NT)
 pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ bins, const int64_t bin_sb,
                           const uint8_t *__restrict__ mask, const float *__restrict__ weights, const int64_t w_sb,
                           const ViewPtrs gp, const int64_t g_sb, int32_t *status,
                           const int B, const int64_t D, const int G, const int tiles_per_shape, const int C,
-                          const int HW)
+                          const int HW, const int num_units)
 {
     constexpr int E = Elem<T>::kVec;
     constexpr int NW = (E + 3) / 4;
     constexpr int P = (V + 7) / 8;
     constexpr int TD = NT * E;
-    __shared__ BwdPlan plan;
+    static_assert(UPC * 32 <= NT, "one planning warp per unit");
+    // A CTA handles UPC consecutive (shape, tile) units: their loads are all in flight before the one barrier, and
+    // warp i plans unit i, so the per-CTA costs (launch slot, barrier, reciprocal table) are paid once per UPC tiles.
+    __shared__ BwdPlan plans[UPC];
     __shared__ float rcp_tab[V + 1];  // rcp_tab[n] = 1 / n, IEEE division
 
-    const int b = blockIdx.x / tiles_per_shape;
-    const int tile = blockIdx.x - b * tiles_per_shape;
-    const int64_t d0 = (int64_t)tile * TD;
+    const int u0 = blockIdx.x * UPC;
     const int e0 = threadIdx.x * E;
-    const bool active = (int64_t)e0 < D - d0;
-    const int64_t off = (int64_t)b * D + d0 + e0;
 
     pdl_wait();
     pdl_launch_dependents();
     // ---- loads first: dS and the tie-mask planes of this thread's elements
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t pwd[P][NW];
-    if (active) {
-        if constexpr (GAP) raw = *reinterpret_cast<const uint4 *>(dS + (int64_t)b * C + (int)((d0 + e0) % C));
-        else raw = ldg_stream_16(dS + off);
-        if constexpr (POOL == GVCNN_POOL_MAX) {
+    uint4 raws[UPC];
+    uint32_t pwds[UPC][P][NW];
+    bool actives[UPC];
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const uint8_t *mp = mask + ((int64_t)p * B) * D + off;
-                if constexpr (E == 8) {
-                    const uint2 w2 = *reinterpret_cast<const uint2 *>(mp);
-                    pwd[p][0] = w2.x;
-                    pwd[p][NW - 1] = w2.y;
-                } else {
-                    pwd[p][0] = *reinterpret_cast<const uint32_t *>(mp);
+    for (int i = 0; i < UPC; ++i) {
+        const int u = u0 + i;
+        const int b = u / tiles_per_shape;
+        const int64_t d0 = (int64_t)(u - b * tiles_per_shape) * TD;
+        actives[i] = u < num_units && (int64_t)e0 < D - d0;
+        const int64_t off = (int64_t)b * D + d0 + e0;
+        raws[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (actives[i]) {
+            if constexpr (GAP) raws[i] = *reinterpret_cast<const uint4 *>(dS + (int64_t)b * C + (int)((d0 + e0) % C));
+            else raws[i] = ldg_stream_16(dS + off);
+            if constexpr (POOL == GVCNN_POOL_MAX) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const uint8_t *mp = mask + ((int64_t)p * B) * D + off;
+                    if constexpr (E == 8) {
+                        const uint2 w2 = *reinterpret_cast<const uint2 *>(mp);
+                        pwds[i][p][0] = w2.x;
+                        pwds[i][p][NW - 1] = w2.y;
+                    } else {
+                        pwds[i][p][0] = *reinterpret_cast<const uint32_t *>(mp);
+                    }
                 }
             }
         }
     }
     if (threadIdx.x <= V && threadIdx.x > 0) rcp_tab[threadIdx.x] = __fdiv_rn(1.0f, (float)threadIdx.x);
 
-    // ---- plan: warp 0 ranks the views by (bin, view)
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+    // ---- plans: warp i ranks the views of unit i by (bin, view)
+    if ((int)(threadIdx.x >> 5) < UPC && u0 + (int)(threadIdx.x >> 5) < num_units) {
+        BwdPlan &plan = plans[threadIdx.x >> 5];
+        const int un = u0 + (int)(threadIdx.x >> 5);
+        const int b = un / tiles_per_shape;
+        const int tile = un - b * tiles_per_shape;
+        const int64_t d0 = (int64_t)tile * TD;
+        const int lane = threadIdx.x & 31;
         int bin = 0x7fffffff;
         if (lane < V) {
             bin = __ldg(bins + (int64_t)b * bin_sb + lane);
@@ -120,8 +134,14 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
         }
     }
     __syncthreads();
-    if (!active) return;
 
+    const uint32_t thread_off = (uint32_t)e0 * (uint32_t)sizeof(T);
+#pragma unroll
+    for (int ui = 0; ui < UPC; ++ui) {
+    if (!actives[ui]) continue;
+    const BwdPlan &plan = plans[ui];
+    const uint4 raw = raws[ui];
+    uint32_t (&pwd)[P][NW] = pwds[ui];
     constexpr bool wts = WTS;  // caller-supplied group weights: compiled out of the default instantiation
     const float sumw = wts ? plan.sumw : (float)(G + V);
     const float rcp_sumw = __frcp_rn((float)(G + V));
@@ -136,7 +156,6 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
         t[e] = wts ? __fdiv_rn(t[e], sumw) : div_by_rcp(t[e], sumw, rcp_sumw);
 
     const uint32_t fm = plan.first_mask;
-    const uint32_t thread_off = (uint32_t)e0 * (uint32_t)sizeof(T);
 
     if constexpr (E == 8 && POOL == GVCNN_POOL_MAX) {
         // bf16: tie bits of an element pair share a register (bits 0..15 / 16..31 = sorted views 0..15
@@ -182,6 +201,31 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             for (int i = 0; i < 4; ++i)
                 ow[i] = val2[i] & prmt_sign((i >> 1) ? sh1 : sh0, (i & 1) ? 0xBBAAu : 0x9988u);
             stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, o);
+        }
+    } else if constexpr (POOL == GVCNN_POOL_MEAN) {
+        // mean: every member of a group receives g1 / n - one value per group, one store per view.  Nothing here needs
+        // a compile-time k, so the walk is a rolled loop (unrolled it was V copies of the group code: 6100 SASS
+        // instructions at V = 20).  g1 / n: n is uniform; for a power of two 1/n is exact and the product is the
+        // correctly rounded quotient (n == 1 included), otherwise the exact division by the reciprocal.
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+            if ((fm >> k) & 1u) {  // uniform: a group starts here (bit 0 is always set)
+                const int n = __popc(plan.seg[k]);
+                const float w = wts ? plan.gw[k] : (float)(1 + n);
+                const float rn = rcp_tab[n];
+                float val[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) val[e] = __fmul_rn(t[e], w);
+                if ((n & (n - 1)) == 0) {  // uniform branch
+#pragma unroll
+                    for (int e = 0; e < E; ++e) val[e] = __fmul_rn(val[e], rn);
+                } else {
+                    div_vec_by_rcp(val, (float)n, rn);
+                }
+                packed = Elem<T>::pack(val);
+            }
+            stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, packed);
         }
     } else {
         // tie bits per element: bit k <=> sorted view k attains its group's max
@@ -231,6 +275,7 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, packed);
         }
     }
+    }  // units
 }
 
 template <typename T, int V, int NT = 256>
@@ -242,16 +287,20 @@ static int launch_bwd_fast_v(const void *dS, const int32_t *bins, int64_t bin_sb
     const int64_t td = (int64_t)NT * E;
     const int64_t tiles = (D + td - 1) / td;
     if ((int64_t)B * tiles > 0x7fffffffLL) return GVCNN_E_BAD_ARG;
-    const unsigned grid = (unsigned)(B * tiles);
+    const int units = (int)(B * tiles);
+    // one unit per CTA: two (the kernel's UPC parameter) measured equal or slower at every size - 70.5 vs 71.7 us at
+    // configs[1], 10.3 vs 12.8 us at 512 shapes (profiles/r03_bwd_units_per_cta_ab.jsonl) - so only UPC = 1 is built
+    constexpr int upc = 1;
+    const unsigned grid = (unsigned)((units + upc - 1) / upc);
     cudaError_t err;
-#define GVCNN_LAUNCH_BF(POOL_, GAP_, WTS_)                                                                    \
-    err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_, WTS_>, dim3(grid), dim3(NT), 0, st,     \
+#define GVCNN_LAUNCH_BF(POOL_, GAP_, WTS_, UPC_)                                                              \
+    err = launch_pdl(pool_fuse_bwd_fast_kernel<T, POOL_, V, NT, GAP_, WTS_, UPC_>, dim3(grid), dim3(NT), 0, st, \
                      static_cast<const T *>(dS), bins, bin_sb, mask, weights, w_sb, gp, g_sb, status, B, D, G,   \
-                     (int)tiles, gapC, gapHW)
+                     (int)tiles, gapC, gapHW, units)
 #define GVCNN_LAUNCH_BF_P(GAP_, WTS_)                                                                         \
     do {                                                                                                      \
-        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, GAP_, WTS_);                              \
-        else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, GAP_, WTS_);                                                    \
+        if (pool == GVCNN_POOL_MAX) GVCNN_LAUNCH_BF(GVCNN_POOL_MAX, GAP_, WTS_, upc);                         \
+        else GVCNN_LAUNCH_BF(GVCNN_POOL_MEAN, GAP_, WTS_, upc);                                               \
     } while (0)
     if (gapC > 0) {
         if (weights) return GVCNN_E_UNSUPPORTED;  // the GAP-folded backward always uses the reference's weights

@@ -23,6 +23,9 @@ cases = [  # B, V, D, G, dtype, pool
     (4, 5, 100, 5, torch.float32, "max"),      # generic one-shot (V not templated), small D
     (2, 12, 7, 8, torch.float32, "mean"),      # scalar fallback (unaligned D)
     (900, 4, 2048, 4, torch.float32, "max"),   # ring, 1800 tiles: ~6 per CTA, ring slots re-used
+    (6, 12, 2048, 8, torch.bfloat16, "mean"),  # bf16 mean walk four rows at a time (mixed-precision adds, reciprocal)
+    (4, 20, 1024, 16, torch.bfloat16, "mean"), # the same on the narrow tiles, V = 20
+    (5, 20, 2048, 16, torch.bfloat16, "max"),  # bf16 backward with three tie planes
 ]
 for B, V, D, G, dt, pool in cases:
     F = torch.relu(torch.randn(B, V, D, device=dev)).to(dt).requires_grad_(True)
@@ -84,6 +87,10 @@ L.gvcnn_host_pipeline_destroy(pipe)
 Fm = [torch.relu(torch.randn(3, 5, 5, 2048, device=dev)).requires_grad_(True) for _ in range(6)]
 out = model.pool_fuse_gap(Fm, torch.randint(0, 10, (3, 6), dtype=torch.int32, device=dev), 10)
 out.sum().backward()
+for Vg in (4, 16, 20):  # the view counts added late in round 2 (one CTA per SM for 16 and 20)
+    Fm = [torch.relu(torch.randn(2, 2, 3, 2048, device=dev)).to(torch.bfloat16).requires_grad_(True) for _ in range(Vg)]
+    out = model.pool_fuse_gap(Fm, torch.randint(0, 8, (2, Vg), dtype=torch.int32, device=dev), 8, pool="mean", empty_fill=0.0)
+    out.float().sum().backward()
 torch.cuda.synchronize()
 # paper mode
 F = torch.relu(torch.randn(6, 12, 512, device=dev)).requires_grad_(True)
