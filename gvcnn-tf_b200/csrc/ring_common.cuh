@@ -77,6 +77,10 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #pragma unroll
     for (int i = 0; i < (V + 3) / 4; ++i)
         skw[i] = __reduce_or_sync(0xffffffffu, reinterpret_cast<const uint32_t *>(plan_s.skip)[i]);
+    // (A rolled, four-rows-at-a-time walk for max pooling WITH the tie planes at V >= 16 - group max parked in the
+    //  ring slot, backward sweep re-reading the rows, or a per-group re-read - was built to get the 55 KB unrolled
+    //  walk under the instruction cache (ncu: hit rate 80 % at bf16 V = 20): bit-identical planes, but 106 / 101 us
+    //  against 82 us for the unrolled walk, profiles/r03_maxmask_chunked_ab.jsonl.  Dropped.)
     // tf.add_n starts from its first term, so the accumulator starts from -0.0f, the identity of IEEE addition
     // (-0 + t == t for every t, signed zeros included).  Empty groups still contribute their term w_g * fill; with
     // fill == 0 and the reference's positive weights each of them is +0 and the walks below skip them.  The one place
