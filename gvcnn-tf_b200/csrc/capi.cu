@@ -5,6 +5,10 @@
 
 #include "comm_dev.cuh"
 
+#ifndef GVCNN_FWD_DIRECT
+#define GVCNN_FWD_DIRECT 1  // GVCNN_FWD_DIRECT=0 in the environment: always the ring (A/B runs)
+#endif
+
 using namespace gvcnn;
 
 namespace {
@@ -264,7 +268,7 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     if (!bins || !S || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
     const int variant = GVCNN_POOL_VARIANT_OF(pool);
     pool &= 0xff;
-    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 3) return GVCNN_E_BAD_MODE;
+    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 4) return GVCNN_E_BAD_MODE;
     const size_t es = elt_size(dtype);
     if (!is_aligned(S, es) || !is_aligned(bins, 4)) return GVCNN_E_MISALIGNED;
     ViewPtrs fp;
@@ -276,9 +280,21 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     al = al && is_aligned(S, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8)) &&
          (!group_desc || is_aligned(group_desc, 16));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
+    if (variant == 4) {  // forced: the one-tile-per-CTA kernel for few views, or nothing
+        if (!al || group_desc || weights) return GVCNN_E_UNSUPPORTED;
+        rc = launch_pool_fuse_fwd_direct(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool, empty_fill, dtype, true,
+                                         static_cast<cudaStream_t>(stream));
+        return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
+    }
     if (al && !group_desc && (variant == 0 || variant == 3)) {
         // fast path: persistent warp-specialised TMA ring (pool_fwd_ring.cu), with the reference's own weights or
         // caller-supplied ones (model.group_fusion's second argument; empty groups then contribute w_g * fill)
+        static const int direct = env_int_once("GVCNN_FWD_DIRECT", GVCNN_FWD_DIRECT);
+        if (direct && !weights && variant == 0) {  // few views: one tile per CTA, no ring (pool_fwd_direct.cu)
+            rc = launch_pool_fuse_fwd_direct(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool, empty_fill, dtype,
+                                             false, static_cast<cudaStream_t>(stream));
+            if (rc != -1000) return rc;
+        }
         rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, weights, weight_stride_b, S, tie_mask, status, B, V, D, G, pool,
                                        empty_fill, dtype, static_cast<cudaStream_t>(stream));
         if (rc != -1000) return rc;
@@ -296,7 +312,7 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     if (!dS || !bins || bin_stride_b < 0) return GVCNN_E_BAD_ARG;
     const int variant = GVCNN_POOL_VARIANT_OF(pool);
     pool &= 0xff;
-    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 3) return GVCNN_E_BAD_MODE;
+    if ((pool != GVCNN_POOL_MAX && pool != GVCNN_POOL_MEAN) || variant > 4) return GVCNN_E_BAD_MODE;
     if (pool == GVCNN_POOL_MAX && !tie_mask) return GVCNN_E_BAD_ARG;
     const size_t es = elt_size(dtype);
     if (!is_aligned(dS, es) || !is_aligned(bins, 4)) return GVCNN_E_MISALIGNED;
@@ -307,7 +323,7 @@ int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_
     if (rc) return rc;
     al = al && is_aligned(dS, 16) && (D * es) % 16 == 0 && (!tie_mask || is_aligned(tie_mask, 8));
     if (weights && (!is_aligned(weights, 4) || weight_stride_b < 0)) return GVCNN_E_BAD_ARG;
-    if (al && (variant == 0 || variant == 3)) {
+    if (al && (variant == 0 || variant == 3 || variant == 4)) {
         // fast path: V-templated kernel (pool_bwd_fast.cu)
         rc = launch_pool_fuse_bwd_fast(dS, bins, bin_stride_b, tie_mask, weights, weight_stride_b, gp, sb, status, B, V, D, G, pool, dtype,
                                        static_cast<cudaStream_t>(stream));

@@ -94,7 +94,8 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
     if constexpr (POOL == GVCNN_POOL_MEAN) {
         uint32_t any_empty = tail_skip;
 #pragma unroll
-        for (int i = 0; i < (V + 3) / 4; ++i) any_empty |= skw[i];
+        for (int i = 0; i < (V + 3) / 4; ++i)  // only the first V bytes of the skip table are written
+            any_empty |= (4 * i + 4 <= V) ? skw[i] : (skw[i] & ((1u << (8 * (V - 4 * i))) - 1u));
         if (!wts && fill == 0.0f && any_empty != 0u) acc0 = 0.0f;
     }
 #pragma unroll

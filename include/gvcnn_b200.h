@@ -61,7 +61,9 @@ extern "C" {
  * (and the matching backward) pooling kernel - 0 = auto (3 when it applies, else 1,
  * else 2), 1 = one tile per CTA, bulk-copy (TMA, cp.async.bulk) staged, 2 = one tile
  * per CTA, plain vector loads staged through shared memory, 3 = persistent
- * warp-specialised TMA ring.  Stateless: the choice travels with the call. */
+ * warp-specialised TMA ring, 4 = one tile per CTA with register loads (few views:
+ * V = 4, 6, 8; GVCNN_E_UNSUPPORTED otherwise; auto picks it where it measured
+ * ahead of the ring).  Stateless: the choice travels with the call. */
 #define GVCNN_POOL_VARIANT(v) ((v) << 8)
 #define GVCNN_POOL_VARIANT_OF(pool) (((pool) >> 8) & 0xf)
 

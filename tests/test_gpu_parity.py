@@ -411,6 +411,36 @@ def test_pool_variants_agree(model, variant, pool, B, V, D, G):
     np.testing.assert_array_equal(x.grad.cpu().numpy(), O.pool_fuse_bwd(dS, F, bins, G, pool))
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("pool,fill", [("max", 1.0), ("mean", 0.0), ("max", 0.0)])
+@pytest.mark.parametrize("B,V,D,G", [(301, 6, 1024, 10), (77, 6, 2048, 8), (90, 4, 2048, 3), (333, 8, 1024, 16),
+                                       (65, 8, 3080, 8), (50, 6, 1032, 2)])
+def test_few_view_kernel_equals_the_ring(model, c_oracle, B, V, D, G, pool, fill, dtype):
+    """pool_fwd_direct.cu (variant 4: one tile per CTA, register loads, rows transposed into sorted order through shared
+    memory) against the persistent ring (variant 3) and the oracle: descriptors and, through the tie planes, gradients
+    bit for bit; full, partial (D = 1032, 3080) and 128-/256-thread tiles, tie-heavy inputs."""
+    F, bins, dS = make_inputs(11 + B + V, B, V, D, G, ties=True)
+    td = torch.float32
+    if dtype == "bf16":
+        F, dS, td = O.round_bf16(F), O.round_bf16(dS), torch.bfloat16
+    outs = []
+    for variant in (4, 3):
+        x = dev(F, td).requires_grad_(True)
+        S = model.pool_fuse(x, dev(bins), G, pool=pool, empty_fill=fill, _variant=variant)
+        S.backward(dev(dS, td))
+        outs.append((S.detach().float().cpu().numpy(), x.grad.float().cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    np.testing.assert_array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    want, wantg = c_oracle.pool_fuse_fwd(F, bins, G, pool, fill), c_oracle.pool_fuse_bwd(dS, F, bins, G, pool)
+    if dtype == "bf16":
+        want, wantg = O.round_bf16(want), O.round_bf16(wantg)
+    np.testing.assert_array_equal(outs[0][0], want)
+    np.testing.assert_array_equal(outs[0][1], wantg)
+    # view counts it is not built for are refused, not silently routed elsewhere
+    with pytest.raises(Exception):
+        model.pool_fuse(dev(np.zeros((2, 12, 1024), np.float32)), dev(np.zeros((2, 12), np.int32)), G, _variant=4)
+
+
 @pytest.mark.parametrize("layout", ["bvd", "vbd", "list"])
 @pytest.mark.parametrize("pool", ["max", "mean"])
 def test_layouts_and_spatial_maps(model, layout, pool):
