@@ -62,12 +62,13 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
 #define GVCNN_MEAN_CHUNKED 1  // A/B builds: 0 = fully unrolled mean walk for every V (round 1)
 #endif
 #ifndef GVCNN_MEAN_CHUNKED_F32
-#define GVCNN_MEAN_CHUNKED_F32 0
+#define GVCNN_MEAN_CHUNKED_F32 0  // A/B builds: 1 = the same walk for float32 at V >= 16 (measured: V = 20 124.4 vs 126.8 us
+                                  // back to back but 178.2 vs 176.0 us in the forward step; V = 16 108.6 vs 95.8 us - stays 0)
 #endif
 #ifndef GVCNN_MEAN_CHUNKED_MINV
 #define GVCNN_MEAN_CHUNKED_MINV 4
 #endif
-    // bf16 only: float32 mean at V = 20 is HBM-bound either way and measured 4 % slower chunked (135.8 vs 129.9 us)
+    // bf16 only: float32 mean is closer to HBM-bound and measured no better on this walk (see GVCNN_MEAN_CHUNKED_F32)
     constexpr bool kChunkedMean = GVCNN_MEAN_CHUNKED && (POOL == GVCNN_POOL_MEAN) && (V % 4 == 0) && V >= GVCNN_MEAN_CHUNKED_MINV && (E == 8 || (GVCNN_MEAN_CHUNKED_F32 && V >= 16));
     // the plan is the same for every thread: pass it through a warp reduction so the compiler keeps it
     // in uniform registers and the per-view branches below are uniform branches
