@@ -258,7 +258,7 @@ def _raw_views(R, layout, c_raw):
     return rv, HW
 
 
-def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulps=1, clamp=False,
+def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulps=4, clamp=False,
               check=True, process_group=None, multiplier=None, status=None, exchange=None,
               global_count=None) -> ScoreResult:
     """Per-view discrimination score and bin.
@@ -276,6 +276,9 @@ def score_bin(R, W, b, num_group, *, score_reduce="shape", layout=None, edge_ulp
        first so every rank bins the same global-batch mean.
     multiplier: None = num_group; 10 = the reference's hard-coded ``score * 10`` (nets/model.py:23;
        'batch' mode only - the fused per-shape kernel multiplies by num_group).
+    edge_ulps: half-width, in float32 ulps of the score, of the band around every bin edge inside which a view is
+       flagged NEAR_EDGE (and by which the a-priori ORDER_EDGE band is widened).  Default 4: the reference composes
+       float32 log and sigmoid kernels where this library does one IEEE division, and the two can differ by a few ulps.
     status: optional persistent int32[4] device tensor the counters are ADDED to (check it every N steps
        with raise_for_status instead of synchronising every step); with check=False and no status given
        nothing is recorded.
@@ -997,7 +1000,7 @@ class _FusedFwdFn(torch.autograd.Function):
 
 def grouping_fusion(raw_view_descriptors, W, b, final_view_descriptors, num_group, pool="max",
                     empty_fill=1.0, score_reduce="shape", layout=None, clamp=False, check=False,
-                    process_group=None, edge_ulps=1, status=None, multiplier=None, exchange=None,
+                    process_group=None, edge_ulps=4, status=None, multiplier=None, exchange=None,
                     global_count=None, _variant=0):
     """The whole hot path with no host hop (replaces the partial_run split of
     train.py:264-288): per-shape mode is one call into the library (score + bin,
