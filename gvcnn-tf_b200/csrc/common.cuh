@@ -302,8 +302,8 @@ __device__ __forceinline__ void mean_of_sum(float (&m)[E], const int n)
 #pragma unroll
         for (int e = 0; e < E; ++e) m[e] = __fmul_rn(m[e], r);
     } else {
-        // (div_by_rcp here instead of the IEEE sequence was measured and dropped: inlined at every group close of the
-        //  unrolled walk it grows the code further, and bf16 mean at V = 20 went from 117 to 150 us)
+        // (the generic kernels keep the IEEE sequence; the ring walks use mean_of_sum_rcp below - with div_by_rcp inlined
+        //  per element at every group close the unrolled walk outgrew the instruction cache: 117 -> 150 us at bf16 V = 20)
         const float fn = (float)n;
 #pragma unroll
         for (int e = 0; e < E; ++e) m[e] = __fdiv_rn(m[e], fn);

@@ -151,9 +151,12 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
 #pragma unroll
         for (int e = 0; e < E; ++e) t[e] = __fdiv_rn(t[e], (float)HW);  // gradient of the mean over positions
     }
+    if constexpr (wts) {  // g0 = dS / sum_w
 #pragma unroll
-    for (int e = 0; e < E; ++e)  // g0 = dS / sum_w
-        t[e] = wts ? __fdiv_rn(t[e], sumw) : div_by_rcp(t[e], sumw, rcp_sumw);
+        for (int e = 0; e < E; ++e) t[e] = __fdiv_rn(t[e], sumw);
+    } else {
+        div_vec_by_rcp(t, sumw, rcp_sumw);  // one range test for the vector, IEEE fall-back out of line
+    }
 
     const uint32_t fm = plan.first_mask;
 
@@ -228,15 +231,13 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
             stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, packed);
         }
     } else {
-        // tie bits per element: bit k <=> sorted view k attains its group's max
+        // max pooling, float32: tie bits per element: bit k <=> sorted view k attains its group's max
         uint32_t me[E];
-        if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                me[e] = 0u;
+        for (int e = 0; e < E; ++e) {
+            me[e] = 0u;
 #pragma unroll
-                for (int p = 0; p < P; ++p) me[e] |= ((pwd[p][e >> 2] >> (8 * (e & 3))) & 0xffu) << (8 * p);
-            }
+            for (int p = 0; p < P; ++p) me[e] |= ((pwd[p][e >> 2] >> (8 * (e & 3))) & 0xffu) << (8 * p);
         }
         float val[E];
         uint4 packed = make_uint4(0u, 0u, 0u, 0u);
@@ -246,32 +247,16 @@ pool_fuse_bwd_fast_kernel(const T *__restrict__ dS, const int32_t *__restrict__ 
                 const uint32_t seg = plan.seg[k];
                 const int n = __popc(seg);
                 const float w = wts ? plan.gw[k] : (float)(1 + n);
-                // mean: g1 / n.  n is uniform; for n a power of two 1/n is exact and the product is the
-                // correctly rounded quotient (n == 1 included), otherwise the exact division by reciprocal
-                if constexpr (POOL == GVCNN_POOL_MAX) {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int nsel = __popc(me[e] & seg);
-                        val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));  // (1 / num_selected) * g1; nsel == 0 only for NaN
-                    }
-                } else {
-                    const float rn = rcp_tab[n];
-                    if ((n & (n - 1)) == 0) {  // uniform branch
-#pragma unroll
-                        for (int e = 0; e < E; ++e) val[e] = __fmul_rn(__fmul_rn(t[e], w), rn);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E; ++e) val[e] = div_by_rcp(__fmul_rn(t[e], w), (float)n, rn);
-                    }
+                for (int e = 0; e < E; ++e) {
+                    const int nsel = __popc(me[e] & seg);
+                    val[e] = __fmul_rn(rcp_tab[nsel], __fmul_rn(t[e], w));  // (1 / num_selected) * g1; nsel == 0 only for NaN
                 }
-                if constexpr (POOL == GVCNN_POOL_MEAN) packed = Elem<T>::pack(val);
             }
-            if constexpr (POOL == GVCNN_POOL_MAX) {
-                float o[E];
+            float o[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) o[e] = (me[e] & (1u << k)) ? val[e] : 0.0f;
-                packed = Elem<T>::pack(o);
-            }
+            for (int e = 0; e < E; ++e) o[e] = (me[e] & (1u << k)) ? val[e] : 0.0f;
+            packed = Elem<T>::pack(o);
             stg_stream_16(reinterpret_cast<char *>(plan.rowptr[k]) + thread_off, packed);
         }
     }

@@ -82,8 +82,7 @@ pool_fuse_fwd_direct_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t
     if (active) {
         const float sumw = (float)(G + V);  // sum_g (1 + n_g): exact in float32 in any order
         const float rcp_sumw = __frcp_rn(sumw);
-#pragma unroll
-        for (int e = 0; e < E; ++e) acc[e] = div_by_rcp(acc[e], sumw, rcp_sumw);
+        div_vec_by_rcp(acc, sumw, rcp_sumw);
         stg_stream_16(S + out_off, Elem<T>::pack(acc));
     }
 }

@@ -212,9 +212,12 @@ pool_fuse_fwd_ring_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
         if (active) {
+            if constexpr (WTS) {
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                acc[e] = WTS ? __fdiv_rn(acc[e], sw_given) : div_by_rcp(acc[e], sumw, rcp_sumw);
+                for (int e = 0; e < E; ++e) acc[e] = __fdiv_rn(acc[e], sw_given);
+            } else {
+                div_vec_by_rcp(acc, sumw, rcp_sumw);  // one range test for the vector, IEEE fall-back out of line
+            }
             stg_stream_16(S + out_off, Elem<T>::pack(acc));
         }
         b += step_b;

@@ -118,9 +118,9 @@ pool_fuse_gap_fwd_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *_
             ring_consume_tile<T, POOL, MASK, V, kRowStride>(col, plans[s], fill, true, mask, B, D, out_off, acc);
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
+            div_vec_by_rcp(acc, sumw, rcp_sumw);  // S at this position, then the running sum over positions
 #pragma unroll
-            for (int e = 0; e < E; ++e)  // S at this position, then the running sum over positions
-                gacc[e] = __fadd_rn(gacc[e], div_by_rcp(acc[e], sumw, rcp_sumw));
+            for (int e = 0; e < E; ++e) gacc[e] = __fadd_rn(gacc[e], acc[e]);
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
         float *dst = partial + ((int64_t)b * NSPLIT + ps) * C + (int64_t)cb * TD + e0;

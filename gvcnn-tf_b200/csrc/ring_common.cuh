@@ -271,7 +271,9 @@ __device__ __forceinline__ void ring_consume_tile(const unsigned char *col, cons
                         raw[kl] = Elem<T>::pack(m);  // exact: m is a max of values of type T
                     }
                     const float w = wts ? plan_s.gw[k - 1] : (float)(1 + cnt);  // acc += w_g * P_g
-                    if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum(m, cnt);
+                    // reciprocal division here too (IEEE sequence out of line): float32 V = 20 mean 127 -> 120 us,
+                    // bf16 V = 6, D = 1024 14.0 -> 13.2 us (profiles/r03_mean_unrolled_rcp_ab.jsonl)
+                    if constexpr (POOL == GVCNN_POOL_MEAN) mean_of_sum_rcp(m, cnt);
                     acc_add_scaled(acc, w, m);
                 }
                 if (fill != 0.0f || wts) {  // empty groups in between / after: w = 1 (or given), P = fill
