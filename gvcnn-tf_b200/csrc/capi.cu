@@ -259,9 +259,14 @@ int gvcnn_gap_score_bin_fwd(const void *maps, const float *W, const float *bias,
     return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
 }
 
-int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b, const float *weights,
-                        int64_t weight_stride_b, void *S, void *group_desc, uint8_t *tie_mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float empty_fill,
-                        int f_layout, int dtype, void *stream)
+// f_ready: the caller launched the kernel(s) directly in front of this one on the stream itself and they do not write
+// F (the score kernels of the one-call entry points).  Every kernel of this library passes griddepcontrol.wait BEFORE
+// it lets its dependents launch, so by the time the pooling kernel can start, whatever produced F earlier on the
+// stream has completed and flushed; the few-view kernel may then issue its loads of F ahead of its own dependency
+// wait, under the tail of the score kernel.  Never true for the public entry point: there the predecessor is unknown.
+static int pool_fuse_fwd_impl(const void *F, const int32_t *bins, int64_t bin_stride_b, const float *weights,
+                              int64_t weight_stride_b, void *S, void *group_desc, uint8_t *tie_mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float empty_fill,
+                              int f_layout, int dtype, bool f_ready, void *stream)
 {
     int rc = check_dims(B, V, D, G, dtype);
     if (rc) return rc == kEmptyBatch ? 0 : rc;
@@ -283,7 +288,7 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     if (variant == 4) {  // forced: the one-tile-per-CTA kernel for few views, or nothing
         if (!al || group_desc || weights) return GVCNN_E_UNSUPPORTED;
         rc = launch_pool_fuse_fwd_direct(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool, empty_fill, dtype, true,
-                                         static_cast<cudaStream_t>(stream));
+                                         f_ready, static_cast<cudaStream_t>(stream));
         return rc == -1000 ? GVCNN_E_UNSUPPORTED : rc;
     }
     if (al && !group_desc && (variant == 0 || variant == 3)) {
@@ -292,7 +297,7 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
         static const int direct = env_int_once("GVCNN_FWD_DIRECT", GVCNN_FWD_DIRECT);
         if (direct && !weights && variant == 0) {  // few views: one tile per CTA, no ring (pool_fwd_direct.cu)
             rc = launch_pool_fuse_fwd_direct(fp, sb, bins, bin_stride_b, S, tie_mask, status, B, V, D, G, pool, empty_fill, dtype,
-                                             false, static_cast<cudaStream_t>(stream));
+                                             false, f_ready, static_cast<cudaStream_t>(stream));
             if (rc != -1000) return rc;
         }
         rc = launch_pool_fuse_fwd_ring(fp, sb, bins, bin_stride_b, weights, weight_stride_b, S, tie_mask, status, B, V, D, G, pool,
@@ -301,6 +306,14 @@ int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b
     }
     return launch_pool_fuse_fwd(fp, sb, bins, bin_stride_b, S, group_desc, tie_mask, weights, weight_stride_b, status, B, V, D, G, pool, empty_fill,
                                 dtype, al, variant, static_cast<cudaStream_t>(stream));
+}
+
+int gvcnn_pool_fuse_fwd(const void *F, const int32_t *bins, int64_t bin_stride_b, const float *weights,
+                        int64_t weight_stride_b, void *S, void *group_desc, uint8_t *tie_mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float empty_fill,
+                        int f_layout, int dtype, void *stream)
+{
+    return pool_fuse_fwd_impl(F, bins, bin_stride_b, weights, weight_stride_b, S, group_desc, tie_mask, status, B, V, D, G, pool,
+                              empty_fill, f_layout, dtype, false, stream);
 }
 
 int gvcnn_pool_fuse_bwd(const void *dS, const int32_t *bins, int64_t bin_stride_b, const float *weights,
@@ -361,8 +374,8 @@ int gvcnn_grouping_fusion_fwd(const void *R, const float *W, const float *bias, 
     rc = gvcnn_score_bin_fwd(R, W, bias, x, scores, bins, flags, status, B, V, C, G, r_layout, dtype, edge_ulps, clamp,
                              stream);
     if (rc) return rc;
-    return gvcnn_pool_fuse_fwd(F, bins, V, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
-                               f_layout, dtype, stream);
+    return pool_fuse_fwd_impl(F, bins, V, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
+                               f_layout, dtype, true, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -391,8 +404,8 @@ int gvcnn_grouping_fusion_batch_fwd(const void *R, const float *W, const float *
     rc = batch_score_tail(empty ? nullptr : x, xsum, x_mean, scores, bins, flags, status, B, V, G, multiplier, edge_ulps,
                           clamp, global_count, exchange, exchange_user, st);
     if (rc || empty) return rc;
-    return gvcnn_pool_fuse_fwd(F, bins, 0, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
-                               f_layout, dtype, stream);
+    return pool_fuse_fwd_impl(F, bins, 0, nullptr, 0, S, nullptr, tie_mask, status, B, V, D, G, pool, empty_fill,
+                               f_layout, dtype, true, stream);
 }
 
 // ---------------------------------------------------------------------------

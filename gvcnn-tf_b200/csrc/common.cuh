@@ -577,7 +577,7 @@ int launch_pool_fuse_fwd_ring(const ViewPtrs &fp, int64_t f_sb, const int32_t *b
                               float fill, int dtype, cudaStream_t st);
 int launch_pool_fuse_fwd_direct(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
                                 uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
-                                int dtype, bool forced, cudaStream_t st);
+                                int dtype, bool forced, bool f_ready, cudaStream_t st);
 size_t gap_workspace_bytes(int B, int C, int HW, int dtype);
 int launch_pool_fuse_gap_fwd(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *out,
                              uint8_t *mask, int32_t *status, float *partial, int B, int V, int HW, int C, int G,

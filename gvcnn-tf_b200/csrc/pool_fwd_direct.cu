@@ -12,7 +12,7 @@
 
 namespace gvcnn {
 
-template <typename T, int POOL, bool MASK, int V, int NT>
+template <typename T, int POOL, bool MASK, int V, int NT, bool EARLY>
 __global__ void __launch_bounds__(NT)
 pool_fuse_fwd_direct_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t *__restrict__ bins,
                             const int64_t bin_sb, T *__restrict__ S, uint8_t *__restrict__ mask, int32_t *status,
@@ -32,14 +32,22 @@ pool_fuse_fwd_direct_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t
     const int64_t out_off = (int64_t)b * D + d0 + e0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    pdl_wait();
-    pdl_launch_dependents();
-    // ---- loads first, natural view order
+    // ---- loads first, natural view order.  EARLY (the one-call entry points only, see pool_fuse_fwd_impl in capi.cu):
+    // F is known to be complete before this grid can start, so its loads go out ahead of the dependency wait and
+    // overlap the tail of the score kernel; bins, S and the tie planes are touched only after the wait.
+    if constexpr (!EARLY) {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
     uint4 raw[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         raw[v] = make_uint4(0u, 0u, 0u, 0u);
         if (active) raw[v] = ldg_stream_16(fp.p[v] + ((int64_t)b * f_sb + d0 + e0) * (int64_t)sizeof(T));
+    }
+    if constexpr (EARLY) {
+        pdl_wait();
+        pdl_launch_dependents();
     }
     // ---- the warp's plan: rank of every view by (bin, view), group starts, empty groups in between
     int bin = 0x7fffffff;
@@ -89,7 +97,7 @@ pool_fuse_fwd_direct_kernel(const ViewPtrs fp, const int64_t f_sb, const int32_t
 
 template <typename T, int V, int NT>
 static int launch_direct_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S, uint8_t *mask,
-                           int32_t *status, int B, int64_t D, int G, int pool, float fill, cudaStream_t st)
+                           int32_t *status, int B, int64_t D, int G, int pool, float fill, bool early, cudaStream_t st)
 {
     constexpr int E = Elem<T>::kVec;
     const int64_t td = (int64_t)NT * E;
@@ -99,12 +107,16 @@ static int launch_direct_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins
     const size_t smem = (size_t)V * NT * 16;
     const bool want_mask = (mask != nullptr) && pool == GVCNN_POOL_MAX;
     cudaError_t err = cudaSuccess;
+#define GVCNN_LAUNCH_DIRECT_E(POOL_, MASK_, EARLY_)                                                          \
+    do {                                                                                                     \
+        err = ensure_dyn_smem<pool_fuse_fwd_direct_kernel<T, POOL_, MASK_, V, NT, EARLY_>>((int)smem);       \
+        if (err == cudaSuccess)                                                                              \
+            err = launch_pdl(pool_fuse_fwd_direct_kernel<T, POOL_, MASK_, V, NT, EARLY_>, dim3(grid), dim3(NT), smem, st, \
+                             fp, f_sb, bins, bin_sb, static_cast<T *>(S), mask, status, B, D, G, fill, (int)tps); \
+    } while (0)
 #define GVCNN_LAUNCH_DIRECT(POOL_, MASK_)                                                                    \
     do {                                                                                                     \
-        err = ensure_dyn_smem<pool_fuse_fwd_direct_kernel<T, POOL_, MASK_, V, NT>>((int)smem);               \
-        if (err == cudaSuccess)                                                                              \
-            err = launch_pdl(pool_fuse_fwd_direct_kernel<T, POOL_, MASK_, V, NT>, dim3(grid), dim3(NT), smem, st, \
-                             fp, f_sb, bins, bin_sb, static_cast<T *>(S), mask, status, B, D, G, fill, (int)tps); \
+        if (early) GVCNN_LAUNCH_DIRECT_E(POOL_, MASK_, true); else GVCNN_LAUNCH_DIRECT_E(POOL_, MASK_, false); \
     } while (0)
     if (pool == GVCNN_POOL_MAX) {
         if (want_mask) GVCNN_LAUNCH_DIRECT(GVCNN_POOL_MAX, true); else GVCNN_LAUNCH_DIRECT(GVCNN_POOL_MAX, false);
@@ -112,13 +124,14 @@ static int launch_direct_v(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins
         GVCNN_LAUNCH_DIRECT(GVCNN_POOL_MEAN, false);
     }
 #undef GVCNN_LAUNCH_DIRECT
+#undef GVCNN_LAUNCH_DIRECT_E
     if (err != cudaSuccess) return (int)err;
     return (int)cudaGetLastError();
 }
 
 template <typename T>
 static int launch_direct_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S, uint8_t *mask,
-                           int32_t *status, int B, int V, int64_t D, int G, int pool, float fill, bool forced, cudaStream_t st)
+                           int32_t *status, int B, int V, int64_t D, int G, int pool, float fill, bool forced, bool early, cudaStream_t st)
 {
     // 128-thread tiles when the descriptor is one of them long (bf16, D = 1024), 256-thread tiles otherwise
     const bool narrow = D <= 128 * Elem<T>::kVec;
@@ -129,8 +142,8 @@ static int launch_direct_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins
     if (!forced && mask != nullptr && pool == GVCNN_POOL_MAX && Elem<T>::kVec == 8 && !narrow && V < 8) return -1000;
 #define GVCNN_DIRECT_CASE(V_)                                                                                          \
     case V_:                                                                                                           \
-        return narrow ? launch_direct_v<T, V_, 128>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st)  \
-                      : launch_direct_v<T, V_, 256>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, st);
+        return narrow ? launch_direct_v<T, V_, 128>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, early, st)  \
+                      : launch_direct_v<T, V_, 256>(fp, f_sb, bins, bin_sb, S, mask, status, B, D, G, pool, fill, early, st);
     switch (V) {
         GVCNN_DIRECT_CASE(4)
         GVCNN_DIRECT_CASE(6)
@@ -143,15 +156,17 @@ static int launch_direct_t(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins
 // returns -1000 when this path does not apply (caller weights, V not in {4, 6, 8}, rows not 16-byte multiples)
 int launch_pool_fuse_fwd_direct(const ViewPtrs &fp, int64_t f_sb, const int32_t *bins, int64_t bin_sb, void *S,
                                 uint8_t *mask, int32_t *status, int B, int V, int64_t D, int G, int pool, float fill,
-                                int dtype, bool forced, cudaStream_t st)
+                                int dtype, bool forced, bool f_ready, cudaStream_t st)
 {
+    static const int env_early = env_int_once("GVCNN_DIRECT_EARLY", 1);  // A/B knob
+    const bool early = f_ready && env_early != 0;
     if (G > 255) return -1000;
     if (dtype == GVCNN_F32) {
         if (D % 4) return -1000;
-        return launch_direct_t<float>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, forced, st);
+        return launch_direct_t<float>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, forced, early, st);
     }
     if (D % 8) return -1000;
-    return launch_direct_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, forced, st);
+    return launch_direct_t<__nv_bfloat16>(fp, f_sb, bins, bin_sb, S, mask, status, B, V, D, G, pool, fill, forced, early, st);
 }
 
 }  // namespace gvcnn
