@@ -56,12 +56,12 @@ def test_algorithmic_bytes_match_baseline_md():
 
 
 def test_committed_cuda_arm_line_has_the_contract_keys():
-    """The CUDA arm cannot run here; the line it printed on the B200 box (profiles/r03i_bench_n1.json) is checked
+    """The CUDA arm cannot run here; the line it printed on the B200 box (profiles/r03p_bench_n1.json) is checked
     against the contract instead, so a change of bench.py's keys without a re-measurement is caught - and against the
-    reference arm's line from the same box (profiles/r03i_bench_reference.json): same config object, like for like."""
-    with open(os.path.join(ROOT, "profiles", "r03i_bench_n1.json")) as f:
+    reference arm's line from the same box (profiles/r03p_bench_reference.json): same config object, like for like."""
+    with open(os.path.join(ROOT, "profiles", "r03p_bench_n1.json")) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
-    with open(os.path.join(ROOT, "profiles", "r03i_bench_reference.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r03p_bench_reference.json")) as f:
         ref = json.loads(f.read().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
